@@ -1,0 +1,87 @@
+"""Pin the CPU oracle against the golden vectors minted from the reference modules
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle.contrastive_oracle import (clip_loss_oracle, dense_labels, soft_label_triples,
+                                       spatial_loss_oracle)
+from spatial_clip_b200.synth import make_spot_batch
+
+
+def _inputs(meta):
+    b = make_spot_batch(**meta["gen"])
+    return (b.image_features.numpy(), b.text_features.numpy(), b.tile_ids.numpy(),
+            b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy())
+
+
+@pytest.mark.parametrize("name", golden_names("spatial"))
+def test_spatial_oracle_matches_reference(name):
+    meta, gold = load_golden(name)
+    img, txt, ids, nbr, alpha = _inputs(meta)
+    c = meta["ctor"]
+    res = spatial_loss_oracle(img, txt, meta["scale"], ids, ids, nbr, alpha, world_size=meta["world"],
+                              cap_logit_scale=c.get("cap_logit_scale"), temp_reg_weight=c.get("temp_reg_weight", 0.0),
+                              neighbor_alpha_scale=c.get("neighbor_alpha_scale", 1.0),
+                              local_loss=c["local_loss"], gather_with_grad=c["gather_with_grad"])
+    loss = np.array([r.loss for r in res.ranks])
+    ds = np.array([r.d_scale for r in res.ranks])
+    # the reference ran in fp32; the oracle in fp64 -> tolerances are the reference's rounding
+    np.testing.assert_allclose(loss, gold["loss"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(ds, gold["d_scale"], rtol=2e-4, atol=2e-6)
+    scale_i = np.abs(gold["d_image"]).max()
+    scale_t = np.abs(gold["d_text"]).max()
+    assert np.abs(res.d_image - gold["d_image"]).max() <= 2e-5 * scale_i + 1e-9
+    assert np.abs(res.d_text - gold["d_text"]).max() <= 2e-5 * scale_t + 1e-9
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("spatial", world=1) if "bias" not in n and "legacy" not in n])
+def test_soft_label_triples_bit_exact(name):
+    meta, gold = load_golden(name)
+    if "labels_i_t" not in gold:
+        pytest.skip("no dense labels stored")
+    _, _, ids, nbr, alpha = _inputs(meta)
+    rows, _ = soft_label_triples(ids, nbr, alpha, meta["ctor"].get("neighbor_alpha_scale", 1.0), rank=0)
+    dense = dense_labels(rows, len(ids))
+    # the reference's labels BEFORE F.normalize(p=1): bit-exact fp32 equality
+    assert dense.dtype == np.float32
+    assert np.array_equal(dense.view(np.uint32), gold["labels_i_t"].view(np.uint32))
+    assert np.array_equal(dense.view(np.uint32), gold["labels_t_i"].view(np.uint32))
+
+
+def test_label_invariants_from_reference_notebook():
+    """The three invariants of /root/reference/notebooks/test1_loss_test.ipynb (cells 1-3)."""
+    b = make_spot_batch(n=48, d=64, k=8, seed=7)
+    ids, nbr, alpha = b.tile_ids.numpy(), b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy()
+    world, bl = 3, 16
+    for r in range(world):
+        sl = slice(r * bl, (r + 1) * bl)
+        rows, sums = soft_label_triples(ids, nbr[sl], alpha[sl], 1.0, rank=r)
+        for i, lst in enumerate(rows):
+            cols = dict(lst)
+            # check 2: own column is rank*B_l + i with weight >= 1
+            assert cols[r * bl + i] >= 1.0
+            # check 1: normalised row sums to 1
+            tot = sum(float(w) for w in cols.values())
+            assert abs(tot / float(sums[i]) - 1.0) < 1e-6
+            # check 3: absent neighbours contribute nothing
+            present = set(ids.tolist())
+            expected = 1.0 + sum(float(a) for nid, a in zip(nbr[sl][i], alpha[sl][i]) if a > 0 and int(nid) in present)
+            assert abs(tot - expected) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names("clip"))
+def test_clip_oracle_matches_reference(name):
+    meta, gold = load_golden(name)
+    img, txt, *_ = _inputs(meta)
+    c = meta["ctor"]
+    res = clip_loss_oracle(img, txt, meta["scale"], world_size=meta["world"], local_loss=c["local_loss"],
+                           gather_with_grad=c["gather_with_grad"])
+    loss = np.array([r.loss for r in res.ranks])
+    ds = np.array([r.d_scale for r in res.ranks])
+    np.testing.assert_allclose(loss, gold["loss"], rtol=5e-6, atol=1e-6)
+    np.testing.assert_allclose(ds, gold["d_scale"], rtol=5e-4, atol=2e-6)  # fp32 reference
+    # floor: the fp32 reference forms (p - 1) with p ~ 1, an absolute error of ~6e-8 * s * c per logit
+    floor = 2e-7 * meta["scale"] / (len(img) // meta["world"])
+    assert np.abs(res.d_image - gold["d_image"]).max() <= 2e-5 * np.abs(gold["d_image"]).max() + floor
+    assert np.abs(res.d_text - gold["d_text"]).max() <= 2e-5 * np.abs(gold["d_text"]).max() + floor
