@@ -1,0 +1,119 @@
+/*
+ * scl_b200.h -- C ABI of the B200-native contrastive-loss hot path (libscl_b200.so).
+ *
+ * The reference (Biogod2020/Spatial-Clip) is pure Python: it has no FFI of its own.  The boundary that
+ * a maintainer binds is its loss-module API,
+ *     SpatialLoss.forward   /root/reference/src/models/components/losses.py:44-124
+ *     ClipLoss.forward      /root/reference/src/models/components/losses.py:131-141
+ *                           /root/reference/src/open_clip/loss.py:132-155
+ *     gather_features       /root/reference/src/open_clip/loss.py:21-65
+ * and every entry point below replaces one group of torch ops inside those functions (cited per
+ * function).  spatial_clip_b200/losses.py binds these with ctypes and re-assembles the two forwards
+ * with the reference's exact parameter names; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named host_*; `stream` is a cudaStream_t passed as void*
+ *   - no function allocates, synchronises the stream, or keeps mutable global state; work areas are
+ *     caller-provided (sizes from the *_plan / *_bytes queries)
+ *   - kernels launch on the calling thread's current CUDA device
+ *   - return 0 on success; SCL_ERR_* (<0) on bad arguments / unsupported shapes;
+ *     -1000 - cudaError_t on a CUDA runtime failure; scl_error_string() decodes all of them
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16
+ *   - feature matrices are row-major [rows, D] with D % 64 == 0 and D <= 512
+ */
+#ifndef SCL_B200_H_
+#define SCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCL_ABI_VERSION 1
+#define SCL_OK 0
+#define SCL_ERR_INVALID_ARG (-1)
+#define SCL_ERR_UNSUPPORTED_SHAPE (-2)
+#define SCL_ERR_NO_DRIVER_ENTRY (-3)
+#define SCL_ERR_TENSOR_MAP (-4)
+#define SCL_ERR_NOT_SM100 (-5)
+
+int scl_abi_version(void);
+const char* scl_error_string(int code);
+/* compute capability must be 10.x; returns SCL_ERR_NOT_SM100 otherwise */
+int scl_check_device(int* num_sms);
+
+/* ---- plans: tile/chunk decomposition and padded extents, pure host arithmetic --------------------- */
+typedef struct scl_plan {
+  int chunks;          /* column chunks (grid.y for fwd, grid.z for bwd)            */
+  int tiles_per_chunk; /* column tiles per chunk                                    */
+  int n_slots;         /* fwd: partial-statistics slots per row (= 2 * chunks)      */
+  int m_pad;           /* rows padded to the 128-row MMA tile                       */
+  int n_pad;           /* columns padded to the column tile                         */
+  int d_split;         /* bwd: number of D slices (1 or 2)                          */
+} scl_plan;
+int scl_fwd_plan(int m_rows, int n_cols, int d, scl_plan* plan);
+int scl_bwd_plan(int m_rows, int n_cols, int d, scl_plan* plan);
+
+/* ---- HBM-bound producer pass --------------------------------------------------------------------
+ * y[rows,d] (bf16) and/or y_t[d,ld_t] (bf16, transposed) from x; normalize != 0 applies
+ * F.normalize(x, dim=-1) first (/root/reference/src/open_clip/model.py:326-345). Either output may be NULL. */
+int scl_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t, int normalize,
+                  void* stream);
+
+/* scalars[0] = min(logit_scale, cap) (cap <= 0: no cap), [1] = scalars[0]*log2(e), [2] = logit_scale
+ * -- forward value of the straight-through cap, losses.py:73-76 */
+int scl_prep_scalars(const float* logit_scale, float cap, float* scalars3, void* stream);
+
+/* ---- soft-target builder (integer path; replaces the dict + Python double loop, losses.py:91-111) ----
+ * all_ids[n_global]: gathered tile ids of the COLUMN modality; nbr_ids/nbr_alpha [b_local, k].
+ * Outputs are ELL lists [b_local, k+1]: pos_col (global column or -1), pos_w (un-normalised fp32
+ * weight, bit-exact vs the reference's dense labels), pos_q (pos_w / max(row sum, 1e-12)).
+ * k == 0 (plain ClipLoss, loss.py:91-102) needs no ids and no work area. */
+size_t scl_positives_workspace_bytes(int n_global);
+int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids, const float* nbr_alpha,
+                        int b_local, int k, float alpha_scale, int rank, void* workspace, size_t workspace_bytes,
+                        int32_t* pos_col, float* pos_w, float* pos_q, void* stream);
+
+/* ---- fused similarity GEMM + online row log-sum-exp (tcgen05) ------------------------------------
+ * x_rows[m_rows,d] x y_cols[n_cols,d]^T, both bf16. partial is float4[plan.n_slots * plan.m_pad].
+ * Replaces matmul + logit_scale multiply + log_softmax/softmax passes: losses.py:78-89,113-121,
+ * loss.py:117-124,150-153.  dbg_z (optional, float[m_rows, dbg_ld]) receives the raw similarities. */
+int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
+                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, void* stream);
+
+/* merge partials and add the positive logits: row_stats[i] = {LSE_i/ln2, E_p[z], Var_p[z], sum_k q_k z_ik} */
+int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int d, const void* x_rows,
+                     const void* y_all, const int32_t* pos_col, const float* pos_q, int k_plus_1, void* row_stats,
+                     void* stream);
+/* sums6 = per-rank sums feeding the loss / gap / d-scale (deterministic single-CTA tree) */
+int scl_reduce_rows(const void* stats_img, const void* stats_txt, int m_rows, const float* scalars3, float* sums6,
+                    void* stream);
+/* out4 = {loss, gap, dloss/dlogit_scale, 2*w*gap}; c = 0.5 / rows-in-the-mean, w = temp_reg_weight
+ * (losses.py:113-122) */
+int scl_loss_scalars(const float* sums6, const float* scalars3, float c, float w, float* out4, void* stream);
+
+/* ---- backward ---------------------------------------------------------------------------------- */
+/* coefficient vectors of dL/dz = P(u_i + v_i z) + Pc(u'_j + v'_j z)  (SURVEY.md 8a closed forms);
+ * col_mode: 0 = no column-direction terms, 1 = only this rank's columns, 2 = all columns */
+int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int n_cols, const scl_plan* plan,
+                   int b_local, int rank, const float* gaps, const float* scalars3, const float* grad_out, float c,
+                   float w, float mult, int col_mode, void* row_coef, void* col_coef, void* stream);
+/* fused recompute + dL/dz + second GEMM (tcgen05): dx_partial float[plan.chunks, plan.m_pad, d];
+ * y_cols_t is the transposed bf16 copy [d, ld_t] of y_cols */
+int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
+                 int d, const float* scalars3, const scl_plan* plan, const void* row_coef, const void* col_coef,
+                 float* dx_partial, void* stream);
+/* sum the chunk partials, add the sparse soft-target terms, cast: dx_out[m_rows, d] in out_dtype
+ * (dx32 is an fp32 work buffer [m_rows, d]; may alias dx_out when out_dtype == 0) */
+int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, int d, const void* y_all,
+                   const int32_t* pos_col, const float* pos_q, int k_plus_1, const int32_t* opp_col_all,
+                   const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
+                   const float* scalars3, const float* grad_out, float c, float w, float mult, int col_mode,
+                   float* dx32, void* dx_out, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCL_B200_H_ */

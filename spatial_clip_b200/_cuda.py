@@ -1,0 +1,235 @@
+"""ctypes binding of libscl_b200.so (include/scl_b200.h) -> ``CudaOps``.
+
+This is the ONLY compute backend of the package.  There is no CPU or eager-PyTorch implementation:
+if the shared library is missing, cannot be loaded, or a tensor is not on a CUDA device, the call
+raises.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libscl_b200.so"
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+class SclPlan(C.Structure):
+    _fields_ = [("chunks", C.c_int), ("tiles_per_chunk", C.c_int), ("n_slots", C.c_int), ("m_pad", C.c_int),
+                ("n_pad", C.c_int), ("d_split", C.c_int)]
+
+
+class SclError(RuntimeError):
+    pass
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "scl_abi_version": (C.c_int, []),
+    "scl_error_string": (C.c_char_p, [C.c_int]),
+    "scl_check_device": (C.c_int, [C.POINTER(C.c_int)]),
+    "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_bwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_cast_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "scl_prep_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "scl_positives_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "scl_build_positives": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                      C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "scl_fwd_rowstats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "scl_row_finalize": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "scl_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scl_loss_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "scl_bwd_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(SclPlan), C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                               C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scl_bwd_finish": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Load libscl_b200.so; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise SclError(
+            f"{_LIB_PATH} is missing. Build it with `python -m spatial_clip_b200.build` "
+            "(nvcc, sm_100a). spatial_clip_b200 has no CPU / eager fallback.")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.scl_abi_version() != 1:
+        raise SclError("libscl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+class CudaOps:
+    """Tensor-level wrappers over the C ABI.  Every method launches on the current stream of the
+    tensors' device and returns without synchronising."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = load_library()
+        self._checked = set()
+
+    # ---------------------------------------------------------------- helpers
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.scl_error_string(rc).decode()
+            raise SclError(f"{what} failed: {msg} (code {rc})")
+
+    def _stream(self, t: torch.Tensor) -> int:
+        if not t.is_cuda:
+            raise SclError("spatial_clip_b200 kernels need CUDA tensors (sm_100a); got a CPU tensor and there is "
+                           "no CPU fallback")
+        idx = t.device.index
+        if idx not in self._checked:
+            with torch.cuda.device(idx):
+                n = C.c_int(0)
+                self._check(self.lib.scl_check_device(C.byref(n)), "scl_check_device")
+            self._checked.add(idx)
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    @staticmethod
+    def empty(shape, dtype, like: torch.Tensor) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=like.device)
+
+    # ---------------------------------------------------------------- plans
+    def fwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
+        p = SclPlan()
+        self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, C.byref(p)), "scl_fwd_plan")
+        return p
+
+    def bwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
+        p = SclPlan()
+        self._check(self.lib.scl_bwd_plan(m_rows, n_cols, d, C.byref(p)), "scl_bwd_plan")
+        return p
+
+    # ---------------------------------------------------------------- ops
+    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
+        st = self._stream(x)
+        rows, d = x.shape
+        y = self.empty((rows, d), torch.bfloat16, x) if want_rows else None
+        y_t = None
+        if want_t:
+            y_t = torch.zeros((d, ld_t), dtype=torch.bfloat16, device=x.device) if ld_t != rows else \
+                self.empty((d, ld_t), torch.bfloat16, x)
+        with torch.cuda.device(x.device):
+            self._check(self.lib.scl_cast_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(y), _ptr(y_t), rows, d, ld_t,
+                                               int(normalize), st), "scl_cast_bf16")
+        return y, y_t
+
+    def prep_scalars(self, logit_scale, cap):
+        st = self._stream(logit_scale)
+        out = self.empty((3,), torch.float32, logit_scale)
+        with torch.cuda.device(logit_scale.device):
+            self._check(self.lib.scl_prep_scalars(_ptr(logit_scale), float(cap) if cap is not None else -1.0,
+                                                  _ptr(out), st), "scl_prep_scalars")
+        return out
+
+    def build_positives(self, all_ids, nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, like):
+        st = self._stream(like)
+        n_global = all_ids.shape[0] if all_ids is not None else 0
+        kp1 = k + 1
+        col = self.empty((b_local, kp1), torch.int32, like)
+        w = self.empty((b_local, kp1), torch.float32, like)
+        q = self.empty((b_local, kp1), torch.float32, like)
+        ws = None
+        ws_bytes = 0
+        if k > 0:
+            ws_bytes = self.lib.scl_positives_workspace_bytes(n_global)
+            ws = self.empty((ws_bytes,), torch.uint8, like)
+        with torch.cuda.device(like.device):
+            self._check(self.lib.scl_build_positives(_ptr(all_ids), max(n_global, b_local), _ptr(nbr_ids),
+                                                     _ptr(nbr_alpha), b_local, k, float(alpha_scale), rank, _ptr(ws),
+                                                     ws_bytes, _ptr(col), _ptr(w), _ptr(q), st),
+                        "scl_build_positives")
+        return col, w, q
+
+    def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
+        st = self._stream(x_rows)
+        m, d = x_rows.shape
+        n = y_cols.shape[0]
+        plan = self.fwd_plan(m, n, d)
+        partial = self.empty((plan.n_slots * plan.m_pad, 4), torch.float32, x_rows)
+        dbg = torch.zeros((m, n), dtype=torch.float32, device=x_rows.device) if debug_z else None
+        with torch.cuda.device(x_rows.device):
+            self._check(self.lib.scl_fwd_rowstats(_ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan),
+                                                  _ptr(partial), _ptr(dbg), n, st), "scl_fwd_rowstats")
+        return (partial, plan, dbg) if debug_z else (partial, plan)
+
+    def row_finalize(self, partial, plan, x_rows, y_all, pos_col, pos_q):
+        st = self._stream(x_rows)
+        m, d = x_rows.shape
+        stats = self.empty((m, 4), torch.float32, x_rows)
+        with torch.cuda.device(x_rows.device):
+            self._check(self.lib.scl_row_finalize(_ptr(partial), C.byref(plan), m, d, _ptr(x_rows), _ptr(y_all),
+                                                  _ptr(pos_col), _ptr(pos_q), pos_col.shape[1], _ptr(stats), st),
+                        "scl_row_finalize")
+        return stats
+
+    def reduce_rows(self, stats_a, stats_b, scalars):
+        st = self._stream(stats_a)
+        sums = self.empty((6,), torch.float32, stats_a)
+        with torch.cuda.device(stats_a.device):
+            self._check(self.lib.scl_reduce_rows(_ptr(stats_a), _ptr(stats_b), stats_a.shape[0], _ptr(scalars),
+                                                 _ptr(sums), st), "scl_reduce_rows")
+        return sums
+
+    def loss_scalars(self, sums6, scalars, c, w):
+        st = self._stream(sums6)
+        out = self.empty((4,), torch.float32, sums6)
+        with torch.cuda.device(sums6.device):
+            self._check(self.lib.scl_loss_scalars(_ptr(sums6), _ptr(scalars), float(c), float(w), _ptr(out), st),
+                        "scl_loss_scalars")
+        return out
+
+    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype):
+        """dX for the local rows: coefficients + fused tensor-core pass + sparse finish."""
+        st = self._stream(x_rows)
+        m, d = x_rows.shape
+        n = y_all.shape[0]
+        plan = self.bwd_plan(m, n, d)
+        row_coef = self.empty((plan.m_pad, 4), torch.float32, x_rows)
+        col_coef = self.empty((plan.n_pad, 4), torch.float32, x_rows)
+        partial = self.empty((plan.chunks, plan.m_pad, d), torch.float32, x_rows)
+        dx32 = self.empty((m, d), torch.float32, x_rows)
+        out = dx32 if out_dtype == torch.float32 else self.empty((m, d), out_dtype, x_rows)
+        with torch.cuda.device(x_rows.device):
+            self._check(self.lib.scl_bwd_coeffs(_ptr(row_stats), m, _ptr(col_stats), n, C.byref(plan), b_local, rank,
+                                                _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c), float(w),
+                                                float(mult), col_mode, _ptr(row_coef), _ptr(col_coef), st),
+                        "scl_bwd_coeffs")
+            self._check(self.lib.scl_bwd_rows(_ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d,
+                                              _ptr(scalars), C.byref(plan), _ptr(row_coef), _ptr(col_coef),
+                                              _ptr(partial), st), "scl_bwd_rows")
+            self._check(self.lib.scl_bwd_finish(_ptr(partial), C.byref(plan), m, d, _ptr(y_all), _ptr(pos_col),
+                                                _ptr(pos_q), pos_col.shape[1], _ptr(opp_col_all), _ptr(opp_q_all), n,
+                                                b_local, rank, _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c),
+                                                float(w), float(mult), col_mode, _ptr(dx32), _ptr(out),
+                                                _DTYPE_CODE[out_dtype], st), "scl_bwd_finish")
+        return out

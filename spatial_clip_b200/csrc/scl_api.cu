@@ -1,0 +1,240 @@
+// extern "C" boundary of libscl_b200.so (see include/scl_b200.h).  Plain pointers and sizes only,
+// no torch types, no allocation, no stream synchronisation, no mutable global state.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "../../include/scl_b200.h"
+#include "scl_kernels.h"
+
+namespace {
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SCL_OK : -1000 - static_cast<int>(e); }
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  // resolved through the runtime so the library has no link-time dependency on libcuda
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return static_cast<EncodeTiledFn>(nullptr);
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, inner] matrix with `ld` elements between rows;
+// box = {64 inner elements (128 B, one swizzle row), box_rows}, SWIZZLE_128B, zero fill out of bounds.
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return SCL_ERR_NO_DRIVER_ENTRY;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return SCL_ERR_INVALID_ARG;
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SCL_OK : SCL_ERR_TENSOR_MAP;
+}
+
+int num_sms_or_default() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;
+  }
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  return sms;
+}
+
+bool shape_ok(int m_rows, int n_cols, int d) { return m_rows >= 1 && n_cols >= 1 && d >= 64 && d <= 512 && d % 64 == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int scl_abi_version(void) { return SCL_ABI_VERSION; }
+
+const char* scl_error_string(int code) {
+  switch (code) {
+    case SCL_OK: return "ok";
+    case SCL_ERR_INVALID_ARG: return "invalid argument (null / misaligned pointer or bad size)";
+    case SCL_ERR_UNSUPPORTED_SHAPE: return "unsupported shape (need D % 64 == 0, 64 <= D <= 512, rows >= 1)";
+    case SCL_ERR_NO_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the CUDA driver";
+    case SCL_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled rejected the tensor map";
+    case SCL_ERR_NOT_SM100: return "device is not compute capability 10.x (kernels are sm_100a only)";
+    default: break;
+  }
+  if (code <= -1000) return cudaGetErrorString(static_cast<cudaError_t>(-code - 1000));
+  return "unknown scl error";
+}
+
+int scl_check_device(int* num_sms) {
+  int dev = 0, major = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_rc(e);
+  if (num_sms) *num_sms = sms;
+  return major == 10 ? SCL_OK : SCL_ERR_NOT_SM100;
+}
+
+int scl_fwd_plan(int m_rows, int n_cols, int d, scl_plan* plan) {
+  if (plan == nullptr) return SCL_ERR_INVALID_ARG;
+  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  int tpc = 0;
+  plan->chunks = scl::fwd_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+  plan->tiles_per_chunk = tpc;
+  plan->n_slots = 2 * plan->chunks;
+  plan->m_pad = (m_rows + 127) / 128 * 128;
+  plan->n_pad = (n_cols + 255) / 256 * 256;
+  plan->d_split = 1;
+  return SCL_OK;
+}
+
+int scl_bwd_plan(int m_rows, int n_cols, int d, scl_plan* plan) {
+  if (plan == nullptr) return SCL_ERR_INVALID_ARG;
+  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  int tpc = 0, nds = 0, dn = 0;
+  scl::bwd_pick_split(d, &nds, &dn);
+  if (dn % 32 != 0) return SCL_ERR_UNSUPPORTED_SHAPE;
+  plan->chunks = scl::bwd_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
+  plan->tiles_per_chunk = tpc;
+  plan->n_slots = 0;
+  plan->m_pad = (m_rows + 127) / 128 * 128;
+  plan->n_pad = (n_cols + 127) / 128 * 128;
+  plan->d_split = nds;
+  return SCL_OK;
+}
+
+int scl_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t, int normalize,
+                  void* stream) {
+  if (x == nullptr || (y == nullptr && y_t == nullptr) || rows < 0 || d <= 0 || d % 64 != 0 || src_dtype < 0 ||
+      src_dtype > 2 || (y_t != nullptr && ld_t < rows))
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_cast_bf16(x, src_dtype, y, y_t, rows, d, ld_t, normalize, static_cast<cudaStream_t>(stream)));
+}
+
+int scl_prep_scalars(const float* logit_scale, float cap, float* scalars3, void* stream) {
+  if (logit_scale == nullptr || scalars3 == nullptr) return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_prep_scalars(logit_scale, cap, scalars3, static_cast<cudaStream_t>(stream)));
+}
+
+size_t scl_positives_workspace_bytes(int n_global) { return scl::positives_hash_bytes(n_global); }
+
+int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids, const float* nbr_alpha,
+                        int b_local, int k, float alpha_scale, int rank, void* workspace, size_t workspace_bytes,
+                        int32_t* pos_col, float* pos_w, float* pos_q, void* stream) {
+  if (b_local < 1 || n_global < b_local || k < 0 || rank < 0 || pos_col == nullptr || pos_w == nullptr ||
+      pos_q == nullptr)
+    return SCL_ERR_INVALID_ARG;
+  if (k > 0 && (all_ids == nullptr || nbr_ids == nullptr || nbr_alpha == nullptr || workspace == nullptr))
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_build_positives(all_ids, n_global, nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank,
+                                             workspace, workspace_bytes, pos_col, pos_w, pos_q,
+                                             static_cast<cudaStream_t>(stream)));
+}
+
+int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
+                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, void* stream) {
+  if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr)
+    return SCL_ERR_INVALID_ARG;
+  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tm_rows, tm_cols;
+  int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
+  if (rc != SCL_OK) return rc;
+  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 256);
+  if (rc != SCL_OK) return rc;
+  return cuda_rc(scl::launch_fwd_rowstats(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks, plan->tiles_per_chunk,
+                                          plan->m_pad, scalars3 + 1, static_cast<float4*>(partial), dbg_z, dbg_ld,
+                                          static_cast<cudaStream_t>(stream)));
+}
+
+int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int d, const void* x_rows,
+                     const void* y_all, const int32_t* pos_col, const float* pos_q, int k_plus_1, void* row_stats,
+                     void* stream) {
+  if (partial == nullptr || plan == nullptr || x_rows == nullptr || y_all == nullptr || pos_col == nullptr ||
+      pos_q == nullptr || row_stats == nullptr || k_plus_1 < 1)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_row_finalize(static_cast<const float4*>(partial), plan->n_slots, plan->m_pad, m_rows, d,
+                                          x_rows, y_all, pos_col, pos_q, k_plus_1, static_cast<float4*>(row_stats),
+                                          static_cast<cudaStream_t>(stream)));
+}
+
+int scl_reduce_rows(const void* stats_img, const void* stats_txt, int m_rows, const float* scalars3, float* sums6,
+                    void* stream) {
+  if (stats_img == nullptr || stats_txt == nullptr || scalars3 == nullptr || sums6 == nullptr || m_rows < 1)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_reduce_rows(static_cast<const float4*>(stats_img), static_cast<const float4*>(stats_txt),
+                                         m_rows, scalars3, sums6, static_cast<cudaStream_t>(stream)));
+}
+
+int scl_loss_scalars(const float* sums6, const float* scalars3, float c, float w, float* out4, void* stream) {
+  if (sums6 == nullptr || scalars3 == nullptr || out4 == nullptr) return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_loss_scalars(sums6, scalars3, c, w, out4, static_cast<cudaStream_t>(stream)));
+}
+
+int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int n_cols, const scl_plan* plan,
+                   int b_local, int rank, const float* gaps, const float* scalars3, const float* grad_out, float c,
+                   float w, float mult, int col_mode, void* row_coef, void* col_coef, void* stream) {
+  if (row_stats == nullptr || col_stats == nullptr || plan == nullptr || gaps == nullptr || scalars3 == nullptr ||
+      grad_out == nullptr || row_coef == nullptr || col_coef == nullptr || b_local < 1 || col_mode < 0 || col_mode > 2)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_bwd_coeffs(static_cast<const float4*>(row_stats), m_rows, plan->m_pad,
+                                        static_cast<const float4*>(col_stats), n_cols, plan->n_pad, b_local, rank, gaps,
+                                        scalars3, grad_out, c, w, mult, col_mode, static_cast<float4*>(row_coef),
+                                        static_cast<float4*>(col_coef), static_cast<cudaStream_t>(stream)));
+}
+
+int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
+                 int d, const float* scalars3, const scl_plan* plan, const void* row_coef, const void* col_coef,
+                 float* dx_partial, void* stream) {
+  if (x_rows == nullptr || y_cols == nullptr || y_cols_t == nullptr || scalars3 == nullptr || plan == nullptr ||
+      row_coef == nullptr || col_coef == nullptr || dx_partial == nullptr || ld_t < n_cols)
+    return SCL_ERR_INVALID_ARG;
+  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  int nds = 0, dn = 0;
+  scl::bwd_pick_split(d, &nds, &dn);
+  CUtensorMap tm_rows, tm_cols, tm_cols_t;
+  int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
+  if (rc != SCL_OK) return rc;
+  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
+  if (rc != SCL_OK) return rc;
+  rc = make_map(&tm_cols_t, y_cols_t, n_cols, d, ld_t, static_cast<uint32_t>(dn));
+  if (rc != SCL_OK) return rc;
+  return cuda_rc(scl::launch_bwd_rows(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
+                                      plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
+                                      static_cast<const float4*>(row_coef), static_cast<const float4*>(col_coef),
+                                      dx_partial, static_cast<cudaStream_t>(stream)));
+}
+
+int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, int d, const void* y_all,
+                   const int32_t* pos_col, const float* pos_q, int k_plus_1, const int32_t* opp_col_all,
+                   const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
+                   const float* scalars3, const float* grad_out, float c, float w, float mult, int col_mode,
+                   float* dx32, void* dx_out, int out_dtype, void* stream) {
+  if (dx_partial == nullptr || plan == nullptr || y_all == nullptr || pos_col == nullptr || pos_q == nullptr ||
+      gaps == nullptr || scalars3 == nullptr || grad_out == nullptr || dx32 == nullptr || k_plus_1 < 1 ||
+      out_dtype < 0 || out_dtype > 2 || (out_dtype != 0 && dx_out == nullptr) ||
+      (col_mode != 0 && (opp_col_all == nullptr || opp_q_all == nullptr)))
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_bwd_finish(dx_partial, plan->chunks, plan->m_pad, m_rows, d, y_all, pos_col, pos_q,
+                                        k_plus_1, opp_col_all, opp_q_all, n_global, b_local, rank, gaps, scalars3,
+                                        grad_out, c, w, mult, col_mode, dx32, dx_out, out_dtype,
+                                        static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Internal launcher declarations shared by the .cu files and the C-ABI layer (scl_api.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace scl {
+
+// ---- tensor-core kernels
+size_t fwd_smem_bytes(int d);
+int fwd_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
+cudaError_t launch_fwd_rowstats(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols, int d,
+                                int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2, float4* partial,
+                                float* dbg_z, int dbg_ld, cudaStream_t stream);
+
+size_t bwd_smem_bytes();
+void bwd_pick_split(int d, int* n_dsplit, int* dn);
+int bwd_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
+cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                            const float* scale_log2, const float4* row_coef, const float4* col_coef,
+                            float* dx_partial, cudaStream_t stream);
+
+// ---- HBM-bound side passes (scl_aux.cu)
+cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t,
+                             int normalize, cudaStream_t stream);
+cudaError_t launch_prep_scalars(const float* logit_scale, float cap, float* scalars, cudaStream_t stream);
+cudaError_t launch_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids,
+                                   const float* nbr_alpha, int b_local, int k, float alpha_scale, int rank,
+                                   void* hash_ws, size_t hash_ws_bytes, int32_t* pos_col, float* pos_w, float* pos_q,
+                                   cudaStream_t stream);
+size_t positives_hash_bytes(int n_global);
+cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, int m_rows, int d, const void* x_rows,
+                                const void* y_all, const int32_t* pos_col, const float* pos_q, int kp1,
+                                float4* row_stats, cudaStream_t stream);
+cudaError_t launch_reduce_rows(const float4* stats_a, const float4* stats_b, int m_rows, const float* scalars,
+                               float* sums6, cudaStream_t stream);
+cudaError_t launch_loss_scalars(const float* sums6, const float* scalars, float c, float w, float* out4,
+                                cudaStream_t stream);
+cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, const float4* col_stats, int n_cols,
+                              int n_pad, int b_local, int rank, const float* gaps, const float* scalars,
+                              const float* grad_out, float c, float w, float mult, int col_mode, float4* row_coef,
+                              float4* col_coef, cudaStream_t stream);
+cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, int m_rows, int d, const void* y_all,
+                              const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
+                              const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
+                              const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
+                              float* dx32, void* dx_out, int out_dtype, cudaStream_t stream);
+
+}  // namespace scl

@@ -1,0 +1,336 @@
+"""Drop-in loss modules for Spatial-Clip's Lightning/Hydra ``train.py`` backed by sm_100a kernels.
+
+Host-side mirror of the reference's loss-module API (same class names, constructor keywords,
+``forward`` parameter NAMES -- the LightningModule dispatches by ``inspect.signature``,
+/root/reference/src/models/spatial_clip_module.py:44,55-64 -- and the same
+``{"contrastive_loss": scalar}`` result):
+
+  * ``SpatialLoss``  <- /root/reference/src/models/components/losses.py:11-124
+  * ``ClipLoss``     <- /root/reference/src/models/components/losses.py:126-141 over
+                        /root/reference/src/open_clip/loss.py:68-155
+  * ``GlobalMappingMultiPositiveClipLoss`` (legacy positional order, bare-tensor return)
+                     <- /root/reference/src/open_clip_train/spatial_loss.py:10-155
+  * feature / id exchange with ``local_loss`` / ``gather_with_grad`` semantics
+                     <- /root/reference/src/open_clip/loss.py:21-65
+
+What differs from the reference, by design:
+  * the [B_l, N] logits, soft labels and softmaxes never exist in HBM; the work is done by the fused
+    tcgen05 kernels reached through the C ABI (``include/scl_b200.h``);
+  * ``gather_with_grad``'s backward reduce-scatter of [N, D] gradients is replaced by an all-gather of
+    per-row statistics (a few floats per row): each rank recomputes its row block and its column
+    block and forms ``d(sum_r loss_r)/d(local features)`` itself -- the same tensor the reference's
+    reduce-scatter delivers;
+  * rank / world size are resolved lazily at the first ``forward`` when not given explicitly (the
+    reference freezes them in ``__init__``, before Lightning creates the process group; pass
+    ``world_size=1`` to reproduce that quirk);
+  * a scalar ``logit_bias`` cancels in both softmaxes and is ignored (zero gradient);
+  * arithmetic: bf16 operands, fp32 accumulation / logits / statistics on chip ("float32_logits" is
+    always on).
+
+The modules hold no parameters and no buffers (checkpoints stay interchangeable).
+No CPU fallback exists: without libscl_b200.so, or with CPU tensors, ``forward`` raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss"]
+
+_OPS = None
+
+
+def _ops():
+    """The compute backend: CUDA kernels behind the C ABI.  (tests may inject a checker backend.)"""
+    global _OPS
+    if _OPS is None:
+        from ._cuda import CudaOps
+
+        _OPS = CudaOps()
+    return _OPS
+
+
+def _set_ops_for_testing(ops):
+    global _OPS
+    prev = _OPS
+    _OPS = ops
+    return prev
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed plumbing (torch.distributed: NCCL on the GPU box, gloo in the CPU tests)
+# ------------------------------------------------------------------------------------------------
+def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    """Rank-major concatenation along dim 0 (== torch.cat(all_gather(...)), loss.py:51-57)."""
+    t = t.contiguous()
+    carrier = t.view(torch.int16) if t.dtype in (torch.bfloat16, torch.float16) else t
+    out = torch.empty((world * carrier.shape[0],) + tuple(carrier.shape[1:]), dtype=carrier.dtype, device=t.device)
+    try:
+        dist.all_gather_into_tensor(out, carrier, group=group)
+    except (RuntimeError, NotImplementedError):
+        parts = [torch.empty_like(carrier) for _ in range(world)]
+        dist.all_gather(parts, carrier, group=group)
+        out = torch.cat(parts, dim=0)
+    return out.view(t.dtype) if carrier is not t else out
+
+
+@dataclass
+class _Cfg:
+    kind: str  # "spatial" | "clip"
+    rank: int
+    world: int
+    local_loss: bool
+    gather_with_grad: bool
+    cap: Optional[float]
+    temp_reg_weight: float
+    alpha_scale: float
+    group: object = None
+
+
+def _col_mode(cfg: _Cfg) -> int:
+    """Which column-direction terms reach the local features (loss.py:49-61).
+
+    2: every column (world 1, differentiable gather, or the global ClipLoss matrix);
+    1: only this rank's own columns (non-differentiable gather with the local slab re-spliced);
+    0: none (non-differentiable gather, local_loss)."""
+    if cfg.world == 1 or cfg.gather_with_grad:
+        return 2
+    if cfg.kind == "clip" and not cfg.local_loss:
+        return 2
+    return 0 if cfg.local_loss else 1
+
+
+class _ContrastiveLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, image_tile_ids, text_tile_ids, neighbor_tile_ids,
+                neighbor_alphas, cfg: _Cfg):
+        ops = _ops()
+        b_local, d = image_features.shape
+        world, rank = cfg.world, cfg.rank
+        n = world * b_local
+        dev = image_features.device
+
+        scale = logit_scale.detach().reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous()
+        scalars = ops.prep_scalars(scale, cfg.cap)
+
+        # ---- features: bf16 copies, gathered rank-major (gather_features, loss.py:21-65)
+        img_l, _ = ops.cast_bf16(image_features.detach().contiguous())
+        txt_l, _ = ops.cast_bf16(text_features.detach().contiguous())
+        if world > 1:
+            img_all = _all_gather_rows(img_l, world, cfg.group)
+            txt_all = _all_gather_rows(txt_l, world, cfg.group)
+        else:
+            img_all, txt_all = img_l, txt_l
+
+        # ---- soft targets as ELL lists (losses.py:91-111); plain CLIP = the diagonal only
+        if cfg.kind == "spatial":
+            k = neighbor_tile_ids.shape[1]
+            same_ids = (image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
+                        and image_tile_ids.shape == text_tile_ids.shape)
+            img_ids = image_tile_ids.to(torch.int64).contiguous()
+            txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
+            if world > 1:  # losses.py:63-68
+                img_ids_all = _all_gather_rows(img_ids, world, cfg.group)
+                txt_ids_all = img_ids_all if same_ids else _all_gather_rows(txt_ids, world, cfg.group)
+            else:
+                img_ids_all, txt_ids_all = img_ids, txt_ids
+            nbr = neighbor_tile_ids.to(torch.int64).contiguous()
+            alpha = neighbor_alphas.to(torch.float32).contiguous()
+            # image rows -> text columns use the text-id map; text rows -> image columns the image-id map
+            col_it, w_it, q_it = ops.build_positives(txt_ids_all, nbr, alpha, b_local, k, cfg.alpha_scale, rank, img_l)
+            if same_ids:
+                col_ti, w_ti, q_ti = col_it, w_it, q_it
+            else:
+                col_ti, w_ti, q_ti = ops.build_positives(img_ids_all, nbr, alpha, b_local, k, cfg.alpha_scale, rank,
+                                                         img_l)
+        else:
+            col_it, w_it, q_it = ops.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
+            col_ti, w_ti, q_ti = col_it, w_it, q_it
+
+        # ---- fused similarity + online LSE, one pass per direction (losses.py:78-89, 113-121)
+        part_i, plan_i = ops.fwd_rowstats(img_l, txt_all, scalars)
+        stats_i = ops.row_finalize(part_i, plan_i, img_l, txt_all, col_it, q_it)
+        part_t, plan_t = ops.fwd_rowstats(txt_l, img_all, scalars)
+        stats_t = ops.row_finalize(part_t, plan_t, txt_l, img_all, col_ti, q_ti)
+
+        sums6 = ops.reduce_rows(stats_i, stats_t, scalars)
+        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
+        if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
+            dist.all_reduce(sums6, op=dist.ReduceOp.SUM, group=cfg.group)
+        c = 0.5 / (n if global_clip else b_local)
+        out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
+
+        ctx.cfg = cfg
+        ctx.c = c
+        ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
+        ctx.scale_shape = logit_scale.shape
+        ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
+                              q_ti)
+        ctx.mark_non_differentiable(col_it, w_it, q_it)
+        return out4[0].clone(), col_it, w_it, q_it
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_unused):
+        ops = _ops()
+        cfg: _Cfg = ctx.cfg
+        (img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti, q_ti) = ctx.saved_tensors
+        world, rank = cfg.world, cfg.rank
+        b_local, d = img_l.shape
+        n = world * b_local
+        go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+
+        # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients
+        if world > 1:
+            kp1 = col_it.shape[1]
+            pack = torch.cat([stats_i, stats_t, col_it.view(torch.float32), q_it, col_ti.view(torch.float32), q_ti,
+                              out4[1:2].expand(b_local, 1)], dim=1).contiguous()
+            allp = _all_gather_rows(pack, world, cfg.group)
+            stats_i_all = allp[:, 0:4].contiguous()
+            stats_t_all = allp[:, 4:8].contiguous()
+            o = 8
+            col_it_all = allp[:, o:o + kp1].contiguous().view(torch.int32)
+            q_it_all = allp[:, o + kp1:o + 2 * kp1].contiguous()
+            col_ti_all = allp[:, o + 2 * kp1:o + 3 * kp1].contiguous().view(torch.int32)
+            q_ti_all = allp[:, o + 3 * kp1:o + 4 * kp1].contiguous()
+            gaps = allp[:, o + 4 * kp1].reshape(world, b_local)[:, 0].contiguous()
+        else:
+            stats_i_all, stats_t_all = stats_i, stats_t
+            col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti
+            gaps = out4[1:2].contiguous()
+
+        mode = _col_mode(cfg)
+        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
+        mult = float(world) if (global_clip and cfg.gather_with_grad) else 1.0
+        w = cfg.temp_reg_weight
+        ld_t = (n + 7) // 8 * 8
+        need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_img = d_txt = d_scale = None
+        if need_i:
+            _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
+            d_img = ops.bwd_rows(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
+                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0])
+        if need_t:
+            _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
+            d_txt = ops.bwd_rows(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
+                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1])
+        if need_s:
+            # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
+            d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)
+        return d_img, d_txt, d_scale, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------------
+class _LossBase(nn.Module):
+    def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod):
+        super().__init__()
+        if use_horovod:
+            raise NotImplementedError("horovod exchange is out of scope; use torch.distributed (NCCL)")
+        self.local_loss = bool(local_loss)
+        self.gather_with_grad = bool(gather_with_grad)
+        self.use_horovod = False
+        self._rank_arg = rank
+        self._world_arg = world_size
+        self.process_group = None
+
+    # rank / world resolution: explicit ctor values win; otherwise ask torch.distributed lazily
+    @property
+    def world_size(self) -> int:
+        if self._world_arg is not None:
+            return int(self._world_arg)
+        return dist.get_world_size(self.process_group) if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def rank(self) -> int:
+        if self._rank_arg is not None:
+            return int(self._rank_arg)
+        return dist.get_rank(self.process_group) if dist.is_available() and dist.is_initialized() else 0
+
+    @staticmethod
+    def _check_features(image_features, text_features, logit_bias):
+        if image_features.dim() != 2 or image_features.shape != text_features.shape:
+            raise ValueError(f"image_features {tuple(image_features.shape)} and text_features "
+                             f"{tuple(text_features.shape)} must both be [B, D]")
+        if logit_bias is not None and torch.as_tensor(logit_bias).numel() != 1:
+            raise NotImplementedError("only a scalar logit_bias is supported (it cancels in both softmaxes)")
+
+    @staticmethod
+    def _scale_tensor(logit_scale, like):
+        if not torch.is_tensor(logit_scale):
+            logit_scale = torch.tensor(float(logit_scale), device=like.device, dtype=torch.float32)
+        return logit_scale
+
+
+class SpatialLoss(_LossBase):
+    """Multi-positive spatial-neighbour CLIP loss (reference: losses.py:11-124)."""
+
+    def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, rank: Optional[int] = None,
+                 world_size: Optional[int] = None, use_horovod: bool = False,
+                 cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod)
+        self.cap_logit_scale = cap_logit_scale
+        self.temp_reg_weight = float(temp_reg_weight or 0.0)
+        self.float32_logits = float32_logits  # logits are always fp32 on chip
+        self.neighbor_alpha_scale = float(neighbor_alpha_scale)
+        self.last_positives = None  # (col, raw weight, normalised weight) ELL lists of the last call
+
+    def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
+                image_tile_ids: torch.Tensor, text_tile_ids: torch.Tensor, neighbor_tile_ids: torch.Tensor,
+                neighbor_alphas: torch.Tensor, logit_bias: Optional[torch.Tensor] = None,
+                output_dict: bool = True) -> Dict[str, torch.Tensor]:
+        self._check_features(image_features, text_features, logit_bias)
+        b = image_features.shape[0]
+        if neighbor_tile_ids.dim() != 2 or neighbor_tile_ids.shape[0] != b or \
+                neighbor_alphas.shape != neighbor_tile_ids.shape or image_tile_ids.shape[0] != b or \
+                text_tile_ids.shape[0] != b:
+            raise ValueError("tile ids must be [B] and neighbour ids / alphas [B, K]")
+        cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
+                   self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group)
+        loss, col, w, q = _ContrastiveLossFn.apply(image_features, text_features,
+                                                   self._scale_tensor(logit_scale, image_features), image_tile_ids,
+                                                   text_tile_ids, neighbor_tile_ids, neighbor_alphas, cfg)
+        self.last_positives = (col, w, q)
+        return {"contrastive_loss": loss}
+
+
+class ClipLoss(_LossBase):
+    """Symmetric InfoNCE (reference: losses.py:126-141 wrapping open_clip loss.py:68-155)."""
+
+    def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, use_horovod: bool = False):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod)
+        self.cache_labels = cache_labels  # labels are implicit (the diagonal); nothing to cache
+
+    def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
+                logit_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        self._check_features(image_features, text_features, logit_bias)
+        cfg = _Cfg("clip", self.rank, self.world_size, self.local_loss, self.gather_with_grad, None, 0.0, 1.0,
+                   self.process_group)
+        loss, _, _, _ = _ContrastiveLossFn.apply(image_features, text_features,
+                                                 self._scale_tensor(logit_scale, image_features), None, None, None,
+                                                 None, cfg)
+        return {"contrastive_loss": loss}
+
+
+class GlobalMappingMultiPositiveClipLoss(SpatialLoss):
+    """Legacy twin with the open_clip_train positional order (reference: spatial_loss.py:37-155)."""
+
+    def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
+                 rank: Optional[int] = 0, world_size: Optional[int] = 1, use_horovod: bool = False,
+                 cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, cap_logit_scale,
+                         temp_reg_weight, float32_logits, neighbor_alpha_scale)
+        self.cache_labels = cache_labels
+
+    def forward(self, image_features, text_features, image_tile_ids, text_tile_ids, neighbor_tile_ids,
+                neighbor_alphas, logit_scale, logit_bias=None, output_dict: bool = False):
+        out = super().forward(image_features, text_features, logit_scale, image_tile_ids, text_tile_ids,
+                              neighbor_tile_ids, neighbor_alphas, logit_bias)
+        return out if output_dict else out["contrastive_loss"]

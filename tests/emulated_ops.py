@@ -1,0 +1,146 @@
+"""TEST-ONLY checker backend: a torch-CPU statement of each C-ABI op's contract (include/scl_b200.h).
+
+It lets the host-side logic of spatial_clip_b200/losses.py (rank resolution, collective order, which
+column terms carry gradient, packing of the statistics exchange) run under gloo on CPU, where the
+CUDA kernels cannot.  It is injected explicitly by tests through ``losses._set_ops_for_testing``;
+nothing in the package imports it and the package has no CPU path of its own.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from oracle.contrastive_oracle import soft_label_triples
+
+LOG2E = 1.4426950408889634
+LN2 = 0.6931471805599453
+
+
+class EmulatedOps:
+    name = "emulated"
+
+    def __init__(self, round_bf16=True):
+        self.round_bf16 = round_bf16
+        self.calls = []
+
+    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
+        self.calls.append("cast_bf16")
+        xf = x.float()
+        if normalize:
+            xf = torch.nn.functional.normalize(xf, dim=-1)
+        y = xf.to(torch.bfloat16) if self.round_bf16 else xf.clone()
+        y_t = None
+        if want_t:
+            y_t = torch.zeros(x.shape[1], ld_t, dtype=y.dtype)
+            y_t[:, : x.shape[0]] = y.t()
+        return (y if want_rows else None), y_t
+
+    def prep_scalars(self, logit_scale, cap):
+        s = float(logit_scale[0])
+        s_eff = min(s, cap) if cap is not None and cap > 0 else s
+        return torch.tensor([s_eff, s_eff * LOG2E, s], dtype=torch.float32)
+
+    def build_positives(self, all_ids, nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, like):
+        self.calls.append("build_positives")
+        kp1 = k + 1
+        col = torch.full((b_local, kp1), -1, dtype=torch.int32)
+        w = torch.zeros(b_local, kp1)
+        q = torch.zeros(b_local, kp1)
+        if k == 0:
+            col[:, 0] = torch.arange(b_local, dtype=torch.int32) + rank * b_local
+            w[:, 0] = 1.0
+            q[:, 0] = 1.0
+            return col, w, q
+        rows, sums = soft_label_triples(all_ids.numpy(), nbr_ids.numpy(), nbr_alpha.numpy(), alpha_scale, rank)
+        for i, lst in enumerate(rows):
+            for t, (c, ww) in enumerate(lst):
+                col[i, t] = c
+                w[i, t] = float(ww)
+                q[i, t] = float(ww) / max(float(sums[i]), 1e-12)
+        return col, w, q
+
+    def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
+        self.calls.append("fwd_rowstats")
+        z = x_rows.double() @ y_cols.double().t()
+        y2 = z * float(scalars[1])
+        m = y2.max(dim=1).values
+        e = torch.exp2(y2 - m[:, None])
+        part = torch.stack([m, e.sum(1), (e * z).sum(1), (e * z * z).sum(1)], dim=1).float()
+        plan = SimpleNamespace(n_slots=1, m_pad=x_rows.shape[0])
+        return (part, plan, z.float()) if debug_z else (part, plan)
+
+    def row_finalize(self, partial, plan, x_rows, y_all, pos_col, pos_q):
+        self.calls.append("row_finalize")
+        m, s0, s1, s2 = partial.double().unbind(1)
+        mu = s1 / s0
+        var = s2 / s0 - mu * mu
+        zq = torch.zeros_like(mu)
+        xd, yd = x_rows.double(), y_all.double()
+        for t in range(pos_col.shape[1]):
+            c = pos_col[:, t].long()
+            ok = c >= 0
+            zz = (xd * yd[c.clamp(min=0)]).sum(1)
+            zq += torch.where(ok, pos_q[:, t].double() * zz, torch.zeros_like(zz))
+        return torch.stack([m + torch.log2(s0), mu, var, zq], dim=1).float()
+
+    def reduce_rows(self, a, b, scalars):
+        s_eff = float(scalars[0])
+        ad, bd = a.double(), b.double()
+        return torch.tensor([
+            (ad[:, 0] * LN2 - s_eff * ad[:, 3]).sum(), (bd[:, 0] * LN2 - s_eff * bd[:, 3]).sum(),
+            (ad[:, 1] - ad[:, 3]).sum(), (bd[:, 1] - bd[:, 3]).sum(), ad[:, 2].sum(), bd[:, 2].sum()],
+            dtype=torch.float32)
+
+    def loss_scalars(self, sums6, scalars, c, w):
+        s = sums6.double()
+        gsum = c * (s[2] + s[3])
+        gap = gsum if w > 0 else 0.0 * gsum
+        loss = c * (s[0] + s[1]) + w * gap * gap
+        ds = gsum + 2 * w * gap * c * (s[4] + s[5])
+        return torch.stack([loss, gap, ds, 2 * w * gap]).float()
+
+    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype):
+        self.calls.append("bwd_rows")
+        m, d = x_rows.shape
+        n = y_all.shape[0]
+        assert torch.equal(y_all_t[:, :n].float(), y_all.t().float())
+        s_eff, s2 = float(scalars[0]), float(scalars[1])
+        g = float(grad_out[0]) * mult * c
+        xd, yd = x_rows.double(), y_all.double()
+        z = xd @ yd.t()
+        rs, cs = row_stats.double(), col_stats.double()
+        gaps = gaps.double()
+        k2r = 2 * w * gaps[rank]
+        u = g * (s_eff + k2r * (1 - s_eff * rs[:, 1]))
+        v = g * k2r * s_eff * torch.ones(m, dtype=torch.float64)
+        owner = torch.arange(n) // b_local
+        on = torch.ones(n, dtype=torch.float64) if col_mode == 2 else (
+            (owner == rank).double() if col_mode == 1 else torch.zeros(n, dtype=torch.float64))
+        k2c = 2 * w * gaps[owner]
+        uc = on * g * (s_eff + k2c * (1 - s_eff * cs[:, 1]))
+        vc = on * g * k2c * s_eff
+        p = torch.exp2(z * s2 - rs[:, 0:1])
+        pc = torch.exp2(z * s2 - cs[None, :, 0])
+        G = p * (u[:, None] + v[:, None] * z) + pc * (uc[None, :] + vc[None, :] * z)
+        dx = G @ yd
+        # sparse soft-target terms
+        coef = g * (s_eff + k2r)
+        for t in range(pos_col.shape[1]):
+            cc = pos_col[:, t].long()
+            ok = (cc >= 0).double()
+            dx -= (coef * ok * pos_q[:, t].double())[:, None] * yd[cc.clamp(min=0)]
+        if col_mode != 0:
+            lo, hi = rank * b_local, (rank + 1) * b_local
+            for t in range(opp_col_all.shape[1]):
+                cc = opp_col_all[:, t].long()
+                sel = (cc >= lo) & (cc < hi)
+                if col_mode == 1:
+                    sel &= owner == rank
+                idx = torch.nonzero(sel).squeeze(1)
+                if idx.numel() == 0:
+                    continue
+                coefj = g * (s_eff + k2c[idx]) * opp_q_all[idx, t].double()
+                dx.index_add_(0, cc[idx] - lo, -(coefj[:, None] * yd[idx]))
+        return dx.to(out_dtype)

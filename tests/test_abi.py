@@ -1,0 +1,48 @@
+"""The C-ABI library loads and exports every symbol include/scl_b200.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from spatial_clip_b200 import build
+    from spatial_clip_b200._cuda import load_library
+
+    build.build()
+    return load_library()
+
+
+def _declared():
+    text = (ROOT / "include/scl_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(scl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from spatial_clip_b200._cuda import EXPORTS
+
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in scl_b200.h but not exported"
+    assert set(names) == set(EXPORTS), "ctypes table and header disagree"
+
+
+def test_plans_and_errors_without_gpu(lib):
+    from spatial_clip_b200._cuda import SclPlan
+
+    assert lib.scl_abi_version() == 1
+    p = SclPlan()
+    assert lib.scl_fwd_plan(4096, 32768, 512, ctypes.byref(p)) == 0
+    assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.chunks * p.tiles_per_chunk >= 32768 // 256
+    assert lib.scl_bwd_plan(300, 300, 512, ctypes.byref(p)) == 0
+    assert p.m_pad == 384 and p.n_pad == 384 and p.d_split == 2
+    assert lib.scl_fwd_plan(128, 128, 96, ctypes.byref(p)) == -2  # D % 64 != 0
+    assert lib.scl_fwd_plan(128, 128, 1024, ctypes.byref(p)) == -2  # D > 512 (this round)
+    assert b"unsupported shape" in lib.scl_error_string(-2)
+    assert lib.scl_positives_workspace_bytes(1000) >= 2048 * 12
