@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Headline benchmark: fused multi-positive CLIP loss fwd+bwd, global batch 32768, D=512, K=8.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = SpatialLoss forward + backward (grads to image features, gene features, logit_scale) over
+one synthetic global batch (SURVEY.md §8d generator), through the reference-facing module API.
+Prints ONE JSON line on rank 0.  Metric/unit/config follow BASELINE.json; ``value`` is whole-job
+pairs/s with inputs resident in HBM, ``e2e`` the same through the module with pinned host buffers
+(H2D of the step's inputs + D2H of the loss inside the timed region), ``roofline`` is for the dominant
+kernel (bwd_rows) from CUDA events recorded around its launches inside the timed region, and
+``cpu_baseline`` is the oracle's torch port of the reference timed on this box's host cores on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_GLOBAL = 32768
+D = 512
+K = 8
+SEED = 1004
+SCALE = 55.0  # cap (40) active, as in a trained run
+SPATIAL_CFG = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+                   neighbor_alpha_scale=0.5, float32_logits=True)  # configs/loss/spatial.yaml
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(burst=float(j["bf16_tflops"]), sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                    hbm=float(j["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's torch port of the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(rows: int, steps: int = 1, warmup: int = 0):
+    """Time the reference's per-rank step (oracle/torch_port.py) for `rows` local rows of the N=32768
+    workload (a W = N/rows rank emulation, one rank timed).  Returns (pairs/s, seconds per step, cores)."""
+    import torch
+
+    from oracle.torch_port import spatial_rank_step
+    from spatial_clip_b200.synth import make_spot_batch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = make_spot_batch(n=N_GLOBAL, d=D, k=K, seed=SEED)
+    sl = slice(0, rows)
+    times = []
+    for it in range(warmup + steps):
+        img_l = b.image_features[sl].clone().requires_grad_(True)
+        txt_l = b.text_features[sl].clone().requires_grad_(True)
+        s = torch.tensor(SCALE, requires_grad=True)
+        t0 = time.perf_counter()
+        spatial_rank_step(img_l, txt_l, b.image_features, b.text_features, s, b.tile_ids, b.neighbor_tile_ids[sl],
+                          b.neighbor_alphas[sl], 0, cap=SPATIAL_CFG["cap_logit_scale"],
+                          temp_reg_weight=SPATIAL_CFG["temp_reg_weight"], alpha_scale=SPATIAL_CFG["neighbor_alpha_scale"])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return rows / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 1024
+    pps, sec, cores = cpu_reference_sample(rows, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = (f"{rows} local rows x N={N_GLOBAL} columns (one rank of a W={N_GLOBAL // rows} emulation of the same "
+              f"workload), fwd+bwd, torch CPU fp32, {cores} threads")
+    line = {
+        "impl": "reference", "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
+        "value": pps, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "SpatialLoss (multi-positive, K=8 neighbours) fwd+bwd, BASELINE configs[2]/[3] loss at the "
+                        "metric's global batch", "global_batch": N_GLOBAL, "embed_dim": D, "k_neighbors": K,
+            "local_batch": N_GLOBAL // n_gpus, "logit_scale": SCALE, **SPATIAL_CFG,
+            "parallelism": f"dp{n_gpus} (row shards, local_loss feature all-gather over NCCL)",
+            "l2": "inputs (134 MB fp32 + 134 MB grads) exceed the 126 MB L2; additionally a 256 MB buffer is "
+                  "written between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from spatial_clip_b200 import SpatialLoss, losses
+    from spatial_clip_b200.synth import make_spot_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    full = make_spot_batch(n=N_GLOBAL, d=D, k=K, seed=SEED)
+    loc = full.rank_slice(rank, world)
+    b_local = N_GLOBAL // world
+    host = dict(img=loc.image_features.pin_memory(), txt=loc.text_features.pin_memory(),
+                ids=loc.tile_ids.pin_memory(), nbr=loc.neighbor_tile_ids.pin_memory(),
+                alpha=loc.neighbor_alphas.pin_memory())
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    scale = torch.tensor(SCALE, device=dev, requires_grad=True)
+    mod = SpatialLoss(**SPATIAL_CFG)
+    ops = losses._ops()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(inp):
+        img = inp["img"].requires_grad_(True)
+        txt = inp["txt"].requires_grad_(True)
+        scale.grad = None
+        out = mod(img, txt, scale, inp["ids"], inp["ids"], inp["nbr"], inp["alpha"])["contrastive_loss"]
+        out.backward()
+        return out, img.grad, txt.grad
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step({k: v.detach() for k, v in dev_in.items()})
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.kernel_events = {}
+    launches0 = ops.launches
+    per_step = []
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush, outside the per-step event pair
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        a.record()
+        loss, _, _ = step({k: v.detach() for k, v in dev_in.items()})
+        b.record()
+        per_step.append((a, b))
+    sync_all()
+    launches = (ops.launches - launches0) // max(1, args.steps)
+    kernel_events, ops.kernel_events = ops.kernel_events, None
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in per_step) / len(per_step)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss_val = float(loss.detach())
+
+    # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> loss D2H, every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    for _ in range(min(2, args.warmup)):
+        l, _, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        float(l.detach().cpu())
+    sync_all()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        l, _, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        l.detach().to("cpu", non_blocking=False)
+    t1.record()
+    sync_all()
+    te = torch.tensor([t0.elapsed_time(t1) / e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    # dominant kernel: bwd_rows, two launches per step (d image, d gene)
+    ev = kernel_events.get("bwd_rows", [])
+    k_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    alg_flops_launch = 2.0 * b_local * N_GLOBAL * D  # the dX GEMM; the z recompute is not algorithmic work
+    achieved = alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    fev = kernel_events.get("fwd_rowstats", [])
+    f_ms = sum(a.elapsed_time(b) for a, b in fev) / max(1, len(fev))
+    pairs_per_s = N_GLOBAL / (ms * 1e-3)
+    step_alg_tflops = (N_GLOBAL / world) / (ms * 1e-3) * 6.0 * N_GLOBAL * D / 1e12  # per GPU, F_alg = 6 N D / pair
+    cpu_pps, cpu_sec, cores = cpu_reference_sample(1024, steps=1, warmup=0)
+
+    line = {
+        "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
+        "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(world),
+        "pairs_per_s_per_gpu": pairs_per_s / world,
+        "loss": loss_val,
+        "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "bwd_rows_kernel", "achieved": achieved, "peak": pk["burst"],
+                     "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": None,
+                     "peak_source": pk["source"], "launch_ms": k_ms, "launches_per_step": len(ev) // max(1, args.steps),
+                     "algorithmic_flops_per_launch": alg_flops_launch,
+                     "frac_of_sustained": achieved / pk["sustained"],
+                     "fwd_rowstats_launch_ms": f_ms,
+                     "fwd_rowstats_tflops": 2.0 * b_local * N_GLOBAL * D / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
+                     "step_algorithmic_tflops_per_gpu": step_alg_tflops,
+                     "step_frac_of_burst": step_alg_tflops / pk["burst"]},
+        "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"1024 local rows x N={N_GLOBAL} columns (one rank of a W=32 emulation), fwd+bwd, "
+                                   f"oracle/torch_port.py (torch CPU fp32), {cpu_sec:.2f} s"},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

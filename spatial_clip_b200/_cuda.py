@@ -94,6 +94,21 @@ class CudaOps:
     def __init__(self):
         self.lib = load_library()
         self._checked = set()
+        self.launches = 0  # kernels launched through this object (bench.py reports it)
+        self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
+
+    def _timed(self, name, device, fn):
+        """Run one C-ABI launch, optionally bracketed by CUDA events on its stream (bench.py roofline)."""
+        if self.kernel_events is None:
+            return fn()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.current_stream(device)
+        a.record(st)
+        rc = fn()
+        b.record(st)
+        self.kernel_events.setdefault(name, []).append((a, b))
+        return rc
 
     # ---------------------------------------------------------------- helpers
     def _check(self, rc: int, what: str):
@@ -140,6 +155,7 @@ class CudaOps:
         with torch.cuda.device(x.device):
             self._check(self.lib.scl_cast_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(y), _ptr(y_t), rows, d, ld_t,
                                                int(normalize), st), "scl_cast_bf16")
+        self.launches += 1
         return y, y_t
 
     def prep_scalars(self, logit_scale, cap):
@@ -148,6 +164,7 @@ class CudaOps:
         with torch.cuda.device(logit_scale.device):
             self._check(self.lib.scl_prep_scalars(_ptr(logit_scale), float(cap) if cap is not None else -1.0,
                                                   _ptr(out), st), "scl_prep_scalars")
+        self.launches += 1
         return out
 
     def build_positives(self, all_ids, nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, like):
@@ -167,6 +184,7 @@ class CudaOps:
                                                      _ptr(nbr_alpha), b_local, k, float(alpha_scale), rank, _ptr(ws),
                                                      ws_bytes, _ptr(col), _ptr(w), _ptr(q), st),
                         "scl_build_positives")
+        self.launches += 3 if k > 0 else 1
         return col, w, q
 
     def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
@@ -177,8 +195,10 @@ class CudaOps:
         partial = self.empty((plan.n_slots * plan.m_pad, 4), torch.float32, x_rows)
         dbg = torch.zeros((m, n), dtype=torch.float32, device=x_rows.device) if debug_z else None
         with torch.cuda.device(x_rows.device):
-            self._check(self.lib.scl_fwd_rowstats(_ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan),
-                                                  _ptr(partial), _ptr(dbg), n, st), "scl_fwd_rowstats")
+            self._check(self._timed("fwd_rowstats", x_rows.device, lambda: self.lib.scl_fwd_rowstats(
+                _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n, st)),
+                "scl_fwd_rowstats")
+        self.launches += 1
         return (partial, plan, dbg) if debug_z else (partial, plan)
 
     def row_finalize(self, partial, plan, x_rows, y_all, pos_col, pos_q):
@@ -189,6 +209,7 @@ class CudaOps:
             self._check(self.lib.scl_row_finalize(_ptr(partial), C.byref(plan), m, d, _ptr(x_rows), _ptr(y_all),
                                                   _ptr(pos_col), _ptr(pos_q), pos_col.shape[1], _ptr(stats), st),
                         "scl_row_finalize")
+        self.launches += 1
         return stats
 
     def reduce_rows(self, stats_a, stats_b, scalars):
@@ -197,6 +218,7 @@ class CudaOps:
         with torch.cuda.device(stats_a.device):
             self._check(self.lib.scl_reduce_rows(_ptr(stats_a), _ptr(stats_b), stats_a.shape[0], _ptr(scalars),
                                                  _ptr(sums), st), "scl_reduce_rows")
+        self.launches += 1
         return sums
 
     def loss_scalars(self, sums6, scalars, c, w):
@@ -205,6 +227,7 @@ class CudaOps:
         with torch.cuda.device(sums6.device):
             self._check(self.lib.scl_loss_scalars(_ptr(sums6), _ptr(scalars), float(c), float(w), _ptr(out), st),
                         "scl_loss_scalars")
+        self.launches += 1
         return out
 
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
@@ -224,12 +247,13 @@ class CudaOps:
                                                 _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c), float(w),
                                                 float(mult), col_mode, _ptr(row_coef), _ptr(col_coef), st),
                         "scl_bwd_coeffs")
-            self._check(self.lib.scl_bwd_rows(_ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d,
-                                              _ptr(scalars), C.byref(plan), _ptr(row_coef), _ptr(col_coef),
-                                              _ptr(partial), st), "scl_bwd_rows")
+            self._check(self._timed("bwd_rows", x_rows.device, lambda: self.lib.scl_bwd_rows(
+                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d, _ptr(scalars), C.byref(plan),
+                _ptr(row_coef), _ptr(col_coef), _ptr(partial), st)), "scl_bwd_rows")
             self._check(self.lib.scl_bwd_finish(_ptr(partial), C.byref(plan), m, d, _ptr(y_all), _ptr(pos_col),
                                                 _ptr(pos_q), pos_col.shape[1], _ptr(opp_col_all), _ptr(opp_q_all), n,
                                                 b_local, rank, _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c),
                                                 float(w), float(mult), col_mode, _ptr(dx32), _ptr(out),
                                                 _DTYPE_CODE[out_dtype], st), "scl_bwd_finish")
+        self.launches += 3 + (1 if col_mode != 0 else 0) + (1 if out_dtype != torch.float32 else 0)
         return out

@@ -85,3 +85,31 @@ def test_clip_oracle_matches_reference(name):
     floor = 2e-7 * meta["scale"] / (len(img) // meta["world"])
     assert np.abs(res.d_image - gold["d_image"]).max() <= 2e-5 * np.abs(gold["d_image"]).max() + floor
     assert np.abs(res.d_text - gold["d_text"]).max() <= 2e-5 * np.abs(gold["d_text"]).max() + floor
+
+
+def test_torch_port_matches_reference_goldens():
+    """The CPU-baseline port (oracle/torch_port.py) reproduces the reference's numbers."""
+    import torch
+
+    from oracle.torch_port import clip_rank_step, spatial_rank_step
+
+    meta, gold = load_golden("spatial_n256_w4")
+    b = make_spot_batch(**meta["gen"])
+    world, bl = 4, 64
+    for r in range(world):
+        sl = slice(r * bl, (r + 1) * bl)
+        img_l = b.image_features[sl].clone().requires_grad_(True)
+        txt_l = b.text_features[sl].clone().requires_grad_(True)
+        s = torch.tensor(meta["scale"], requires_grad=True)
+        loss = spatial_rank_step(img_l, txt_l, b.image_features, b.text_features, s, b.tile_ids,
+                                 b.neighbor_tile_ids[sl], b.neighbor_alphas[sl], r)
+        np.testing.assert_allclose(float(loss), gold["loss"][r], rtol=2e-6)
+        np.testing.assert_allclose(float(s.grad), gold["d_scale"][r], rtol=1e-4, atol=1e-6)
+    meta, gold = load_golden("clip_n128_w1_s14")
+    b = make_spot_batch(**meta["gen"])
+    img = b.image_features.clone().requires_grad_(True)
+    txt = b.text_features.clone().requires_grad_(True)
+    s = torch.tensor(meta["scale"], requires_grad=True)
+    loss = clip_rank_step(img, txt, img, txt, s, 0)
+    np.testing.assert_allclose(float(loss), gold["loss"][0], rtol=2e-6)
+    assert np.abs(img.grad.numpy() - gold["d_image"]).max() <= 1e-5 * np.abs(gold["d_image"]).max()
