@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 run() {
   name=$1; shift
   echo "=== $name"
-  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -p no:cacheprovider "$@" > gpurun_out/$name.log 2>&1
+  timeout 420 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 200 -p no:cacheprovider "$@" > gpurun_out/$name.log 2>&1
   echo "exit $?"; tail -n 25 gpurun_out/$name.log
 }
 run l1_similarity -k similarity

@@ -160,7 +160,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
         sums6 = ops.reduce_rows(stats_i, stats_t, scalars)
         global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
-            dist.all_reduce(sums6, op=dist.ReduceOp.SUM, group=cfg.group)
+            # all-gather + fixed-order sum (bitwise identical on every rank, unlike an all-reduce tree)
+            sums6 = _all_gather_rows(sums6.reshape(1, 6), world, cfg.group).sum(dim=0)
         c = 0.5 / (n if global_clip else b_local)
         out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
 
