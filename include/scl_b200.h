@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SCL_ABI_VERSION 1
+#define SCL_ABI_VERSION 2
 #define SCL_OK 0
 #define SCL_ERR_INVALID_ARG (-1)
 #define SCL_ERR_UNSUPPORTED_SHAPE (-2)
@@ -51,10 +51,12 @@ typedef struct scl_plan {
   int n_slots;         /* fwd: partial-statistics slots per row (= 2 * chunks)      */
   int m_pad;           /* rows padded to the 128-row MMA tile                       */
   int n_pad;           /* columns padded to the column tile                         */
-  int d_split;         /* bwd: number of D slices (1 or 2)                          */
+  int d_split;         /* bwd: number of D slices (1 or 2; always 1 for the CTA-pair kernel) */
+  int variant;         /* 0 = single-CTA kernels (cta_group::1), 1 = CTA-pair kernels (cta_group::2) */
 } scl_plan;
-int scl_fwd_plan(int m_rows, int n_cols, int d, scl_plan* plan);
-int scl_bwd_plan(int m_rows, int n_cols, int d, scl_plan* plan);
+/* variant: 0 / 1 as above, -1 = library default (environment SCL_VARIANT=0|1 overrides the default) */
+int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan);
+int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan);
 
 /* ---- HBM-bound producer pass --------------------------------------------------------------------
  * y[rows,d] (bf16) and/or y_t[d,ld_t] (bf16, transposed) from x; normalize != 0 applies
@@ -96,16 +98,20 @@ int scl_loss_scalars(const float* sums6, const float* scalars3, float c, float w
 
 /* ---- backward ---------------------------------------------------------------------------------- */
 /* coefficient vectors of dL/dz = P(u_i + v_i z) + Pc(u'_j + v'_j z)  (SURVEY.md 8a closed forms);
- * col_mode: 0 = no column-direction terms, 1 = only this rank's columns, 2 = all columns */
+ * col_mode: 0 = no column-direction terms, 1 = only this rank's columns, 2 = all columns.
+ * pos_q / opp_q_local [b_local, k_plus_1]: the local rows' soft-target weights in the row direction and in the
+ * opposite direction; slot 0 (the row's own column) goes into row_coef[i].w and is subtracted on chip */
 int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int n_cols, const scl_plan* plan,
                    int b_local, int rank, const float* gaps, const float* scalars3, const float* grad_out, float c,
-                   float w, float mult, int col_mode, void* row_coef, void* col_coef, void* stream);
+                   float w, float mult, int col_mode, const float* pos_q, const float* opp_q_local, int k_plus_1,
+                   void* row_coef, void* col_coef, void* stream);
 /* fused recompute + dL/dz + second GEMM (tcgen05): dx_partial float[plan.chunks, plan.m_pad, d];
- * y_cols_t is the transposed bf16 copy [d, ld_t] of y_cols */
+ * y_cols_t is the transposed bf16 copy [d, ld_t] of y_cols; diag_col0 = global column of local row 0
+ * (rank * b_local, the ground-truth offset of losses.py:94 / loss.py:95-96) */
 int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
-                 int d, const float* scalars3, const scl_plan* plan, const void* row_coef, const void* col_coef,
-                 float* dx_partial, void* stream);
-/* sum the chunk partials, add the sparse soft-target terms, cast: dx_out[m_rows, d] in out_dtype
+                 int d, int diag_col0, const float* scalars3, const scl_plan* plan, const void* row_coef,
+                 const void* col_coef, float* dx_partial, void* stream);
+/* sum the chunk partials, add the neighbour (slot >= 1) soft-target terms, cast: dx_out[m_rows, d] in out_dtype
  * (dx32 is an fp32 work buffer [m_rows, d]; may alias dx_out when out_dtype == 0) */
 int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, int d, const void* y_all,
                    const int32_t* pos_col, const float* pos_q, int k_plus_1, const int32_t* opp_col_all,

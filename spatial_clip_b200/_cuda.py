@@ -18,7 +18,7 @@ _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 class SclPlan(C.Structure):
     _fields_ = [("chunks", C.c_int), ("tiles_per_chunk", C.c_int), ("n_slots", C.c_int), ("m_pad", C.c_int),
-                ("n_pad", C.c_int), ("d_split", C.c_int)]
+                ("n_pad", C.c_int), ("d_split", C.c_int), ("variant", C.c_int)]
 
 
 class SclError(RuntimeError):
@@ -30,8 +30,8 @@ EXPORTS = {
     "scl_abi_version": (C.c_int, []),
     "scl_error_string": (C.c_char_p, [C.c_int]),
     "scl_check_device": (C.c_int, [C.POINTER(C.c_int)]),
-    "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
-    "scl_bwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_bwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
     "scl_cast_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
     "scl_prep_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
@@ -47,9 +47,9 @@ EXPORTS = {
     "scl_loss_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "scl_bwd_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(SclPlan), C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_void_p]),
-    "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                               C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scl_bwd_finish": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
@@ -73,7 +73,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 1:
+    if lib.scl_abi_version() != 2:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -94,6 +94,7 @@ class CudaOps:
     def __init__(self):
         self.lib = load_library()
         self._checked = set()
+        self.variant = -1  # -1: library default (env SCL_VARIANT), 0: single-CTA kernels, 1: CTA-pair kernels
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
 
@@ -135,12 +136,12 @@ class CudaOps:
     # ---------------------------------------------------------------- plans
     def fwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
         p = SclPlan()
-        self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, C.byref(p)), "scl_fwd_plan")
+        self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, self.variant, C.byref(p)), "scl_fwd_plan")
         return p
 
     def bwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
         p = SclPlan()
-        self._check(self.lib.scl_bwd_plan(m_rows, n_cols, d, C.byref(p)), "scl_bwd_plan")
+        self._check(self.lib.scl_bwd_plan(m_rows, n_cols, d, self.variant, C.byref(p)), "scl_bwd_plan")
         return p
 
     # ---------------------------------------------------------------- ops
@@ -231,7 +232,7 @@ class CudaOps:
         return out
 
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
-                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype):
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
         """dX for the local rows: coefficients + fused tensor-core pass + sparse finish."""
         st = self._stream(x_rows)
         m, d = x_rows.shape
@@ -242,13 +243,17 @@ class CudaOps:
         partial = self.empty((plan.chunks, plan.m_pad, d), torch.float32, x_rows)
         dx32 = self.empty((m, d), torch.float32, x_rows)
         out = dx32 if out_dtype == torch.float32 else self.empty((m, d), out_dtype, x_rows)
+        if opp_q_local is None:  # single rank: the gathered opposite list IS the local one
+            opp_q_local = opp_q_all[rank * b_local:(rank + 1) * b_local]
         with torch.cuda.device(x_rows.device):
             self._check(self.lib.scl_bwd_coeffs(_ptr(row_stats), m, _ptr(col_stats), n, C.byref(plan), b_local, rank,
                                                 _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c), float(w),
-                                                float(mult), col_mode, _ptr(row_coef), _ptr(col_coef), st),
+                                                float(mult), col_mode, _ptr(pos_q), _ptr(opp_q_local),
+                                                pos_col.shape[1], _ptr(row_coef), _ptr(col_coef), st),
                         "scl_bwd_coeffs")
             self._check(self._timed("bwd_rows", x_rows.device, lambda: self.lib.scl_bwd_rows(
-                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d, _ptr(scalars), C.byref(plan),
+                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d, rank * b_local, _ptr(scalars),
+                C.byref(plan),
                 _ptr(row_coef), _ptr(col_coef), _ptr(partial), st)), "scl_bwd_rows")
             self._check(self.lib.scl_bwd_finish(_ptr(partial), C.byref(plan), m, d, _ptr(y_all), _ptr(pos_col),
                                                 _ptr(pos_q), pos_col.shape[1], _ptr(opp_col_all), _ptr(opp_q_all), n,

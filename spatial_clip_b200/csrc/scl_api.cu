@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/scl_b200.h"
 #include "scl_kernels.h"
@@ -58,6 +59,14 @@ int num_sms_or_default() {
   return sms;
 }
 
+constexpr int kDefaultVariant = 0;
+int resolve_variant(int variant) {
+  if (variant == 0 || variant == 1) return variant;
+  const char* e = std::getenv("SCL_VARIANT");
+  if (e != nullptr && (e[0] == '0' || e[0] == '1') && e[1] == 0) return e[0] - '0';
+  return kDefaultVariant;
+}
+
 bool shape_ok(int m_rows, int n_cols, int d) { return m_rows >= 1 && n_cols >= 1 && d >= 64 && d <= 512 && d % 64 == 0; }
 
 }  // namespace
@@ -92,31 +101,44 @@ int scl_check_device(int* num_sms) {
   return major == 10 ? SCL_OK : SCL_ERR_NOT_SM100;
 }
 
-int scl_fwd_plan(int m_rows, int n_cols, int d, scl_plan* plan) {
+int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0;
-  plan->chunks = scl::fwd_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+  plan->variant = resolve_variant(variant);
+  if (plan->variant == 1) {
+    plan->chunks = scl::fwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+    plan->m_pad = (m_rows + 255) / 256 * 256;
+  } else {
+    plan->chunks = scl::fwd_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+    plan->m_pad = (m_rows + 127) / 128 * 128;
+  }
   plan->tiles_per_chunk = tpc;
   plan->n_slots = 2 * plan->chunks;
-  plan->m_pad = (m_rows + 127) / 128 * 128;
   plan->n_pad = (n_cols + 255) / 256 * 256;
   plan->d_split = 1;
   return SCL_OK;
 }
 
-int scl_bwd_plan(int m_rows, int n_cols, int d, scl_plan* plan) {
+int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0, nds = 0, dn = 0;
-  scl::bwd_pick_split(d, &nds, &dn);
-  if (dn % 32 != 0) return SCL_ERR_UNSUPPORTED_SHAPE;
-  plan->chunks = scl::bwd_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
-  plan->tiles_per_chunk = tpc;
-  plan->n_slots = 0;
+  plan->variant = resolve_variant(variant);
   plan->m_pad = (m_rows + 127) / 128 * 128;
-  plan->n_pad = (n_cols + 127) / 128 * 128;
-  plan->d_split = nds;
+  plan->n_slots = 0;
+  if (plan->variant == 1) {
+    plan->chunks = scl::bwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+    plan->n_pad = (n_cols + 255) / 256 * 256;
+    plan->d_split = 1;
+  } else {
+    scl::bwd_pick_split(d, &nds, &dn);
+    if (dn % 32 != 0) return SCL_ERR_UNSUPPORTED_SHAPE;
+    plan->chunks = scl::bwd_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
+    plan->n_pad = (n_cols + 127) / 128 * 128;
+    plan->d_split = nds;
+  }
+  plan->tiles_per_chunk = tpc;
   return SCL_OK;
 }
 
@@ -156,8 +178,13 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
   CUtensorMap tm_rows, tm_cols;
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
-  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 256);
+  rc = make_map(&tm_cols, y_cols, d, n_cols, d, plan->variant == 1 ? 128 : 256);
   if (rc != SCL_OK) return rc;
+  if (plan->variant == 1)
+    return cuda_rc(scl::launch_fwd_rowstats_pair(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks,
+                                                 plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
+                                                 static_cast<float4*>(partial), dbg_z, dbg_ld,
+                                                 static_cast<cudaStream_t>(stream)));
   return cuda_rc(scl::launch_fwd_rowstats(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks, plan->tiles_per_chunk,
                                           plan->m_pad, scalars3 + 1, static_cast<float4*>(partial), dbg_z, dbg_ld,
                                           static_cast<cudaStream_t>(stream)));
@@ -189,19 +216,22 @@ int scl_loss_scalars(const float* sums6, const float* scalars3, float c, float w
 
 int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int n_cols, const scl_plan* plan,
                    int b_local, int rank, const float* gaps, const float* scalars3, const float* grad_out, float c,
-                   float w, float mult, int col_mode, void* row_coef, void* col_coef, void* stream) {
+                   float w, float mult, int col_mode, const float* pos_q, const float* opp_q_local, int k_plus_1,
+                   void* row_coef, void* col_coef, void* stream) {
   if (row_stats == nullptr || col_stats == nullptr || plan == nullptr || gaps == nullptr || scalars3 == nullptr ||
-      grad_out == nullptr || row_coef == nullptr || col_coef == nullptr || b_local < 1 || col_mode < 0 || col_mode > 2)
+      grad_out == nullptr || row_coef == nullptr || col_coef == nullptr || b_local < 1 || col_mode < 0 ||
+      col_mode > 2 || pos_q == nullptr || opp_q_local == nullptr || k_plus_1 < 1 || m_rows > b_local)
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_bwd_coeffs(static_cast<const float4*>(row_stats), m_rows, plan->m_pad,
                                         static_cast<const float4*>(col_stats), n_cols, plan->n_pad, b_local, rank, gaps,
-                                        scalars3, grad_out, c, w, mult, col_mode, static_cast<float4*>(row_coef),
-                                        static_cast<float4*>(col_coef), static_cast<cudaStream_t>(stream)));
+                                        scalars3, grad_out, c, w, mult, col_mode, pos_q, opp_q_local, k_plus_1,
+                                        static_cast<float4*>(row_coef), static_cast<float4*>(col_coef),
+                                        static_cast<cudaStream_t>(stream)));
 }
 
 int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
-                 int d, const float* scalars3, const scl_plan* plan, const void* row_coef, const void* col_coef,
-                 float* dx_partial, void* stream) {
+                 int d, int diag_col0, const float* scalars3, const scl_plan* plan, const void* row_coef,
+                 const void* col_coef, float* dx_partial, void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || y_cols_t == nullptr || scalars3 == nullptr || plan == nullptr ||
       row_coef == nullptr || col_coef == nullptr || dx_partial == nullptr || ld_t < n_cols)
     return SCL_ERR_INVALID_ARG;
@@ -209,6 +239,19 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
   int nds = 0, dn = 0;
   scl::bwd_pick_split(d, &nds, &dn);
   CUtensorMap tm_rows, tm_cols, tm_cols_t;
+  if (plan->variant == 1) {
+    int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 64);
+    if (rc != SCL_OK) return rc;
+    rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
+    if (rc != SCL_OK) return rc;
+    rc = make_map(&tm_cols_t, y_cols_t, n_cols, d, ld_t, 128);
+    if (rc != SCL_OK) return rc;
+    return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
+                                             plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
+                                             static_cast<const float4*>(row_coef),
+                                             static_cast<const float4*>(col_coef), dx_partial,
+                                             static_cast<cudaStream_t>(stream)));
+  }
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
   rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
@@ -216,7 +259,7 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
   rc = make_map(&tm_cols_t, y_cols_t, n_cols, d, ld_t, static_cast<uint32_t>(dn));
   if (rc != SCL_OK) return rc;
   return cuda_rc(scl::launch_bwd_rows(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
-                                      plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
+                                      plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
                                       static_cast<const float4*>(row_coef), static_cast<const float4*>(col_coef),
                                       dx_partial, static_cast<cudaStream_t>(stream)));
 }

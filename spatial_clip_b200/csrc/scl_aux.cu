@@ -347,13 +347,16 @@ cudaError_t launch_loss_scalars(const float* sums6, const float* scalars, float 
 // =====================================================================================
 // backward coefficient vectors
 // =====================================================================================
-// row_coef[i] = {Lr, u_i, v_i, 0},  col_coef[j] = {Lc, u'_j, v'_j, 0}  with
+// row_coef[i] = {Lr, u_i, v_i, t_i},  col_coef[j] = {Lc, u'_j, v'_j, 0}  with
+//   t_i = g * c * (s_eff + k2) * (q_own[i][0] + q_opp[i][0]): the soft-target weight on the row's own column
+//         (slot 0 of both ELL lists), subtracted inside the tensor-core kernel before bf16 rounding
 //   u = g * c * (s_eff + k2 * (1 - s_eff * mu)),  v = g * c * k2 * s_eff,  k2 = 2 * w * gap(owner rank)
 // g = upstream grad * mult.  col_mode: 0 none, 1 only columns owned by `rank`, 2 all columns.
 __global__ void bwd_coeffs_kernel(const float4* __restrict__ row_stats, int m_rows, int m_pad,
                                   const float4* __restrict__ col_stats, int n_cols, int n_pad, int b_local, int rank,
                                   const float* __restrict__ gaps, const float* __restrict__ scalars,
                                   const float* __restrict__ grad_out, float c, float w, float mult, int col_mode,
+                                  const float* __restrict__ pos_q, const float* __restrict__ opp_q_local, int kp1,
                                   float4* __restrict__ row_coef, float4* __restrict__ col_coef) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float s_eff = scalars[0];
@@ -363,7 +366,9 @@ __global__ void bwd_coeffs_kernel(const float4* __restrict__ row_stats, int m_ro
     if (i < m_rows) {
       const float4 st = row_stats[i];
       const float k2 = 2.f * w * gaps[rank];
-      o = make_float4(st.x, g * (s_eff + k2 * (1.f - s_eff * st.y)), g * k2 * s_eff, 0.f);
+      float qd = pos_q[static_cast<size_t>(i) * kp1];
+      if (col_mode != 0) qd += opp_q_local[static_cast<size_t>(i) * kp1];
+      o = make_float4(st.x, g * (s_eff + k2 * (1.f - s_eff * st.y)), g * k2 * s_eff, g * (s_eff + k2) * qd);
     }
     row_coef[i] = o;
   }
@@ -382,19 +387,20 @@ __global__ void bwd_coeffs_kernel(const float4* __restrict__ row_stats, int m_ro
 }
 cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, const float4* col_stats, int n_cols,
                               int n_pad, int b_local, int rank, const float* gaps, const float* scalars,
-                              const float* grad_out, float c, float w, float mult, int col_mode, float4* row_coef,
-                              float4* col_coef, cudaStream_t stream) {
+                              const float* grad_out, float c, float w, float mult, int col_mode, const float* pos_q,
+                              const float* opp_q_local, int kp1, float4* row_coef, float4* col_coef,
+                              cudaStream_t stream) {
   const int n = max(m_pad, n_pad);
   bwd_coeffs_kernel<<<(n + 255) / 256, 256, 0, stream>>>(row_stats, m_rows, m_pad, col_stats, n_cols, n_pad, b_local,
-                                                         rank, gaps, scalars, grad_out, c, w, mult, col_mode, row_coef,
-                                                         col_coef);
+                                                         rank, gaps, scalars, grad_out, c, w, mult, col_mode, pos_q,
+                                                         opp_q_local, kp1, row_coef, col_coef);
   return cudaGetLastError();
 }
 
 // =====================================================================================
 // backward finish: chunk partial sums + sparse soft-target terms + cast
 // =====================================================================================
-// warp per local row:  dx32[i,:] = sum_chunks partial  -  g*c*(s_eff + k2_rank) * sum_k q_ik * Y[col_ik,:]
+// warp per local row:  dx32[i,:] = sum_chunks partial  -  g*c*(s_eff + k2_rank) * sum_{k>=1} q_ik * Y[col_ik,:]
 __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
                                                          int m_rows, int d, const __nv_bfloat16* __restrict__ y_all,
                                                          const int* __restrict__ pos_col,
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
           *reinterpret_cast<const float4*>(dx_partial + (static_cast<size_t>(ch) * m_pad + row) * d + c0);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
-    for (int t = 0; t < kp1; ++t) {
+    for (int t = 1; t < kp1; ++t) {  // slot 0 (own column) is handled inside bwd_rows_kernel
       const int col = pos_col[static_cast<size_t>(row) * kp1 + t];
       if (col < 0) continue;
       const float qc = -coef * pos_q[static_cast<size_t>(row) * kp1 + t];
@@ -441,6 +447,7 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict_
   const int lane = threadIdx.x & 31;
   if (e >= static_cast<long long>(n_global) * kp1) return;
   const int j = static_cast<int>(e / kp1);
+  if (e % kp1 == 0) return;  // slot 0 (own column) is handled inside bwd_rows_kernel
   const int col = opp_col_all[e];
   if (col < rank * b_local || col >= (rank + 1) * b_local) return;
   const int owner = j / b_local;

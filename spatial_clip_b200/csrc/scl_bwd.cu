@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 bwd_rows_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 128}
                 const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
                 const __grid_constant__ CUtensorMap tm_cols_t,  // Y^T [D, N]  box {64, DN}
-                int m_rows, int n_cols, int d, int dn, int n_tiles, int tiles_per_chunk, int m_pad,
+                int m_rows, int n_cols, int d, int dn, int n_tiles, int tiles_per_chunk, int m_pad, int diag0,
                 const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
                 const float4* __restrict__ col_coef, float* __restrict__ dx_partial) {
   extern __shared__ uint8_t smem_raw[];
@@ -176,7 +176,12 @@ bwd_rows_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  b
     const int h = (warp - 4) >> 2;  // 64-column half of the tile == G sub-tile index
     const int r_loc = q * 32 + lane;
     const float s2 = __ldg(scale_log2_ptr);
-    const float4 rc = __ldg(&row_coef[row0 + r_loc]);  // {Lr (log2 units), u, v, -}
+    const float4 rc = __ldg(&row_coef[row0 + r_loc]);  // {Lr (log2 units), u, v, diagonal soft-target term}
+    // The row's own column (weight >= 1/2 of the soft target, P ~ 1 near convergence) is subtracted here, in
+    // fp32 BEFORE the bf16 rounding of G: done later in fp32 against the rounded dense value it would cancel
+    // catastrophically (net (P - 1) vs an absolute rounding error of 2^-9 * P).
+    const int diag_col = diag0 + row0 + r_loc;
+    const int warp_diag_lo = diag0 + row0 + q * 32;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
@@ -191,6 +196,8 @@ bwd_rows_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  b
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kBwdZCol + buf * kBwdBN + h * 64 + c * 32, r);
         tmem_ld_wait();
         uint32_t packed[16];
+        const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
+        const int di = has_diag ? diag_col - col0 : -1;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float g2[2];
@@ -203,6 +210,7 @@ bwd_rows_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  b
             const float pc = ex2_approx(y - cc.x);
             float g = p * fmaf(rc.z, z, rc.y);
             g = fmaf(pc, fmaf(cc.z, z, cc.y), g);
+            if (has_diag) g -= (j + e == di) ? rc.w : 0.f;
             g2[e] = (col0 + j + e < n_cols) ? g : 0.f;
           }
           packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
@@ -269,7 +277,7 @@ int bwd_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_c
 }
 
 cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
-                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                             const float* scale_log2, const float4* row_coef, const float4* col_coef,
                             float* dx_partial, cudaStream_t stream) {
   int n_dsplit, dn;
@@ -282,7 +290,7 @@ cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_co
   const int n_tiles = (n_cols + kBwdBN - 1) / kBwdBN;
   dim3 grid(row_blocks, n_dsplit, chunks);
   bwd_rows_kernel<<<grid, kBwdThreads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, dn, n_tiles,
-                                                       tiles_per_chunk, m_pad, scale_log2, row_coef, col_coef,
+                                                       tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
                                                        dx_partial);
   return cudaGetLastError();
 }

@@ -1,0 +1,315 @@
+// Backward row-gradient kernel, CTA-pair version (tcgen05 cta_group::2, cluster of 2 CTAs).
+//
+// Same contract as bwd_rows_kernel (scl_bwd.cu):  dX[i,:] = sum_j G_ij Y[j,:],
+//   G_ij = P_ij (u_i + v_i z_ij) + Pc_ij (u'_j + v'_j z_ij) - [j == own column] t_i,
+// but organised so that the similarity tile is recomputed exactly ONCE per (row block, column tile):
+// a CTA pair owns 128 rows (64 per CTA).  With UMMA M = 128 across two SMs each SM keeps a 64-row slice
+// of every accumulator in the "2x2" TMEM layout (64 rows x N as 128 lanes x N/2 columns: lanes 64..127
+// hold the upper half of N), so per SM
+//   dX accumulator  [64 x 512] fp32 = 2 groups x 128 columns     (TMEM columns   0..255)
+//   z tile          [64 x 256] fp32 =            128 columns x 2 (TMEM columns 256..511, double buffered)
+// fit together -- which a single SM with 128 rows cannot do at D = 512 (the single-CTA kernel splits D
+// and recomputes z twice).  G is written once per CTA ([64 x 256] bf16) and both GEMMs are issued by
+// the leader CTA's MMA thread with cta_group::2.
+//
+// Barriers (same smem offset in both CTAs): x_full, full[s], tmem_empty[b], g_full[b] are waited on by
+// the leader (TMA bytes / remote arrivals from the peer are credited to the leader's copy); empty[s],
+// tmem_full[b], g_empty[b], acc_full are multicast by the leader's tcgen05.commit to both CTAs.
+#include "scl_kernels.h"
+#include "scl_ptx.cuh"
+
+namespace scl {
+
+constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
+constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
+constexpr int kB2BK = 64;
+constexpr int kB2Stages = 6;
+constexpr int kB2StageBytes = 16384;
+constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
+constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
+constexpr int kB2GBytes = 4 * kB2GSubBytes;           // 32 KB per buffer
+constexpr int kB2Threads = 384;
+constexpr int kB2ZCol = 256;
+
+struct B2Bars {
+  uint64_t x_full;
+  uint64_t full[kB2Stages];
+  uint64_t empty[kB2Stages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t g_full[2];
+  uint64_t g_empty[2];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
+bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
+                     const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
+                     const __grid_constant__ CUtensorMap tm_cols_t,  // Y^T [D, N]  box {64, 128}
+                     int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad, int diag0,
+                     const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
+                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ B2Bars bars;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nk = d / kB2BK;
+  uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
+  uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 2 x 32 KB
+  uint8_t* smem_ring = smem_g + 2 * kB2GBytes;           // 6 x 16 KB
+
+  const int ng = (d + 255) / 256;  // accumulator groups of up to 256 output columns
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int pair_row0 = (blockIdx.x >> 1) * 128;
+  const int row0 = pair_row0 + static_cast<int>(cta) * kB2Rows;
+  const int t_begin = blockIdx.y * tiles_per_chunk;
+  const int t_end = min(t_begin + tiles_per_chunk, n_tiles);
+  const int n_my = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_rows);
+    tma_prefetch_desc(&tm_cols);
+    tma_prefetch_desc(&tm_cols_t);
+    mbar_init(&bars.x_full, 1);
+    for (int s = 0; s < kB2Stages; ++s) {
+      mbar_init(&bars.full[s], 1);
+      mbar_init(&bars.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars.tmem_full[b], 1);
+      mbar_init(&bars.tmem_empty[b], 16);
+      mbar_init(&bars.g_full[b], 16);
+      mbar_init(&bars.g_empty[b], 1);
+    }
+    mbar_init(&bars.acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(&bars.tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one thread per CTA)
+    if (lane == 0) {
+      if (leader) mbar_arrive_expect_tx(&bars.x_full, static_cast<uint32_t>(2 * nk * kB2XChunkBytes));
+      for (int kc = 0; kc < nk; ++kc)
+        tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
+      int it = 0;
+      auto acquire = [&]() {
+        const int s = it % kB2Stages;
+        mbar_wait(&bars.empty[s], ((it / kB2Stages) & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kB2StageBytes);
+        ++it;
+        return s;
+      };
+      auto push_z = [&](int lt) {
+        const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
+        for (int kc = 0; kc < nk; ++kc) {
+          const int s = acquire();
+          tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+        }
+      };
+      auto push_yt = [&](int lt) {
+        const int col0 = (t_begin + lt) * kB2TileN;
+        for (int js = 0; js < 4; ++js)
+          for (int g = 0; g < ng; ++g) {
+            const int n_g = min(256, d - 256 * g);
+            const int s = acquire();
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols_t, &bars.full[s], col0 + js * 64,
+                             256 * g + static_cast<int>(cta) * (n_g / 2));
+          }
+      };
+      push_z(0);
+      for (int lt = 0; lt < n_my; ++lt) {
+        if (lt + 1 < n_my) push_z(lt + 1);
+        push_yt(lt);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
+      mbar_wait(&bars.x_full, 0);
+      tc_fence_after();
+      int it = 0;
+      auto issue_z = [&](int lt) {
+        const int buf = lt & 1;
+        mbar_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % kB2Stages;
+          mbar_wait(&bars.full[s], (it / kB2Stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_x + kc * kB2XChunkBytes);
+          const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16_pair(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
+                             idesc_z, (kc | k) != 0 ? 1u : 0u);
+          tc_commit_pair(&bars.empty[s]);
+        }
+        tc_commit_pair(&bars.tmem_full[buf]);
+      };
+      auto issue_acc = [&](int lt) {
+        const int gbuf = lt & 1;
+        mbar_wait(&bars.g_full[gbuf], (lt >> 1) & 1);
+        tc_fence_after();
+        for (int js = 0; js < 4; ++js)
+          for (int g = 0; g < ng; ++g, ++it) {
+            const int n_g = min(256, d - 256 * g);
+            const uint32_t idesc_acc = umma_idesc_bf16(128, n_g);
+            const int s = it % kB2Stages;
+            mbar_wait(&bars.full[s], (it / kB2Stages) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_g + gbuf * kB2GBytes + js * kB2GSubBytes);
+            const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16_pair(tmem_base + g * 128, umma_desc_kmajor_sw128(a_addr + k * 32),
+                               umma_desc_kmajor_sw128(b_addr + k * 32), idesc_acc, (lt | js | k) != 0 ? 1u : 0u);
+            tc_commit_pair(&bars.empty[s]);
+          }
+        tc_commit_pair(&bars.g_empty[gbuf]);
+      };
+      issue_z(0);
+      for (int lt = 0; lt < n_my; ++lt) {
+        if (lt + 1 < n_my) issue_z(lt + 1);
+        issue_acc(lt);
+      }
+      tc_commit_pair(&bars.acc_full);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: z -> G (bf16, swizzled smem)
+    const int q = warp & 3;          // TMEM lane quadrant
+    const int h = (warp - 4) >> 2;   // which 64 of this quadrant's 128 columns
+    const int r_loc = (q & 1) * 32 + lane;  // row within this CTA's 64 (2x2 layout: lanes 64.. = upper N half)
+    const int n_half = q >> 1;
+    const int js = n_half * 2 + h;   // 64-column G sub-tile this warp produces
+    const float s2 = __ldg(scale_log2_ptr);
+    const float4 rc = __ldg(&row_coef[row0 + r_loc]);  // {Lr, u, v, own-column soft-target term}
+    const int diag_col = diag0 + row0 + r_loc;
+    const int warp_diag_lo = diag0 + row0 + (q & 1) * 32;
+    for (int lt = 0; lt < n_my; ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
+      mbar_wait(&bars.g_empty[buf], ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* g_row = smem_g + buf * kB2GBytes + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = (t_begin + lt) * kB2TileN + js * 64 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + h * 64 + c * 32, r);
+        tmem_ld_wait();
+        uint32_t packed[16];
+        const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
+        const int di = has_diag ? diag_col - col0 : -1;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float g2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float z = __uint_as_float(r[j + e]);
+            const float4 cc = __ldg(&col_coef[col0 + j + e]);  // warp-uniform address
+            const float y = z * s2;
+            const float p = ex2_approx(y - rc.x);
+            const float pc = ex2_approx(y - cc.x);
+            float g = p * fmaf(rc.z, z, rc.y);
+            g = fmaf(pc, fmaf(cc.z, z, cc.y), g);
+            if (has_diag) g -= (j + e == di) ? rc.w : 0.f;
+            g2[e] = (col0 + j + e < n_cols) ? g : 0.f;
+          }
+          packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (c * 4 + ch) ^ (r_loc & 7);
+          *reinterpret_cast<uint4*>(g_row + chunk * 16) =
+              make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) {
+          mbar_arrive(&bars.tmem_empty[buf]);
+          mbar_arrive(&bars.g_full[buf]);
+        } else {
+          mbar_arrive_remote(&bars.tmem_empty[buf], 0);
+          mbar_arrive_remote(&bars.g_full[buf], 0);
+        }
+      }
+    }
+    // ---- drain this CTA's 64-row slice of the dX accumulators
+    mbar_wait(&bars.acc_full, 0);
+    tc_fence_after();
+    float* out_row = dx_partial + (static_cast<size_t>(blockIdx.y) * m_pad + row0 + r_loc) * d;
+    for (int g = 0; g < ng; ++g) {
+      const int n_g = min(256, d - 256 * g);
+      const int n_ch = n_g / 64;  // 32-column chunks in this lane half's n_g / 2 columns
+      const int c_begin = h == 0 ? 0 : n_ch / 2;
+      const int c_end = h == 0 ? n_ch / 2 : n_ch;
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + c * 32, r);
+        tmem_ld_wait();
+        float* dst = out_row + 256 * g + n_half * (n_g / 2) + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+size_t bwd_pair_smem_bytes(int d) {
+  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + 2 * kB2GBytes + kB2Stages * kB2StageBytes;
+}
+
+int bwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {
+  const int pairs = (m_rows + 127) / 128;
+  const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
+  const int pair_slots = num_sms / 2;
+  int chunks = (6 * pair_slots + pairs - 1) / pairs;
+  chunks = max(1, min(chunks, max(1, n_tiles / 4)));
+  int tpc = (n_tiles + chunks - 1) / chunks;
+  chunks = (n_tiles + tpc - 1) / tpc;
+  *tiles_per_chunk = tpc;
+  return chunks;
+}
+
+cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+                                 int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
+                                 const float* scale_log2, const float4* row_coef, const float4* col_coef,
+                                 float* dx_partial, cudaStream_t stream) {
+  const size_t smem = bwd_pair_smem_bytes(d);
+  cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  const int pairs = (m_rows + 127) / 128;
+  const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
+  dim3 grid(2 * pairs, chunks);
+  bwd_rows_pair_kernel<<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, n_tiles,
+                                                           tiles_per_chunk, m_pad, diag0, scale_log2, row_coef,
+                                                           col_coef, dx_partial);
+  return cudaGetLastError();
+}
+
+}  // namespace scl

@@ -1,0 +1,226 @@
+// Forward row-statistics kernel, CTA-pair version (tcgen05 cta_group::2, cluster of 2 CTAs).
+//
+// Same contract as fwd_rowstats_kernel (scl_fwd.cu) -- online row max / sum / first and second moments of
+// z = X . Y^T -- but one UMMA instruction spans two SMs: the pair owns 256 rows (128 per CTA), each CTA
+// loads only ITS half of every 256-column Y tile (16 KB per K-chunk instead of 32 KB), and the leader
+// CTA's single MMA thread issues 256x256x16 instructions that read both CTAs' shared memory.  Halving
+// the per-SM operand traffic frees shared memory for a 6-deep TMA ring (the 3-deep ring of the
+// single-CTA kernel left the tensor pipe waiting on TMA ~1/3 of the time, profiles/r1_*).
+//
+// Barrier protocol (all barriers live at the same smem offset in both CTAs):
+//   a_full, full[s]   waited on by the leader only; both CTAs' TMA loads credit the LEADER's barrier
+//   empty[s]          each CTA's producer waits on its own copy; the leader's tcgen05.commit multicasts
+//   tmem_full[b]      each CTA's epilogue waits on its own copy (multicast commit)
+//   tmem_empty[b]     leader only, 16 arrivals: the 8 epilogue warps of both CTAs (peer arrives remotely)
+#include "scl_kernels.h"
+#include "scl_ptx.cuh"
+
+namespace scl {
+
+constexpr int kF2Rows = 128;        // rows per CTA (256 per pair)
+constexpr int kF2TileN = 256;       // columns per tile (128 loaded by each CTA)
+constexpr int kF2BK = 64;
+constexpr int kF2Stages = 6;
+constexpr int kF2Threads = 384;
+constexpr int kF2AChunkBytes = kF2Rows * kF2BK * 2;  // 16 KB
+constexpr int kF2BStageBytes = 128 * kF2BK * 2;      // 16 KB (this CTA's half of the tile)
+
+struct F2Bars {
+  uint64_t a_full;
+  uint64_t full[kF2Stages];
+  uint64_t empty[kF2Stages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
+fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, D], box {64, 128}
+                         const __grid_constant__ CUtensorMap tm_cols,  // Y [N, D], box {64, 128}
+                         int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad,
+                         const float* __restrict__ scale_log2_ptr, float4* __restrict__ partial,
+                         float* __restrict__ dbg_z, int dbg_ld) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ F2Bars bars;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nk = d / kF2BK;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + nk * kF2AChunkBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int row0 = (blockIdx.x >> 1) * 256 + static_cast<int>(cta) * kF2Rows;
+  const int t_begin = blockIdx.y * tiles_per_chunk;
+  const int t_end = min(t_begin + tiles_per_chunk, n_tiles);
+  const int n_my = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_rows);
+    tma_prefetch_desc(&tm_cols);
+    mbar_init(&bars.a_full, 1);
+    for (int s = 0; s < kF2Stages; ++s) {
+      mbar_init(&bars.full[s], 1);
+      mbar_init(&bars.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars.tmem_full[b], 1);
+      mbar_init(&bars.tmem_empty[b], 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(&bars.tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one thread per CTA)
+    if (lane == 0) {
+      if (leader) mbar_arrive_expect_tx(&bars.a_full, static_cast<uint32_t>(2 * nk * kF2AChunkBytes));
+      for (int kc = 0; kc < nk; ++kc)
+        tma_load_2d_pair(smem_a + kc * kF2AChunkBytes, &tm_rows, &bars.a_full, kc * kF2BK, row0);
+      int it = 0;
+      for (int lt = 0; lt < n_my; ++lt) {
+        const int col0 = (t_begin + lt) * kF2TileN + static_cast<int>(cta) * 128;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % kF2Stages;
+          mbar_wait(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kF2BStageBytes);
+          tma_load_2d_pair(smem_b + s * kF2BStageBytes, &tm_cols, &bars.full[s], kc * kF2BK, col0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
+      mbar_wait(&bars.a_full, 0);
+      tc_fence_after();
+      int it = 0;
+      for (int lt = 0; lt < n_my; ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kF2TileN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % kF2Stages;
+          mbar_wait(&bars.full[s], (it / kF2Stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + kc * kF2AChunkBytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * kF2BStageBytes);
+#pragma unroll
+          for (int k = 0; k < kF2BK / 16; ++k)
+            tc_mma_bf16_pair(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
+                             idesc, (kc | k) != 0 ? 1u : 0u);
+          tc_commit_pair(&bars.empty[s]);
+        }
+        tc_commit_pair(&bars.tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const int row = row0 + q * 32 + lane;
+    const float s2 = __ldg(scale_log2_ptr);
+    float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
+    for (int lt = 0; lt < n_my; ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      const int tile_col0 = (t_begin + lt) * kF2TileN + h * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = tile_col0 + c * 32;
+        if (col0 >= n_cols) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kF2TileN + h * 128 + c * 32, r);
+        tmem_ld_wait();
+        const int n_valid = min(32, n_cols - col0);
+        float y[32];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(r[j]);
+          y[j] = (j < n_valid) ? x * s2 : -INFINITY;
+          cm = fmaxf(cm, y[j]);
+        }
+        const float m_new = fmaxf(m, cm);
+        const float sc = ex2_approx(m - m_new);
+        s_e *= sc;
+        s_ez *= sc;
+        s_ezz *= sc;
+        m = m_new;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(r[j]);
+          const float e = ex2_approx(y[j] - m);
+          s_e += e;
+          const float t = e * x;
+          s_ez += t;
+          s_ezz = fmaf(t, x, s_ezz);
+        }
+        if (dbg_z != nullptr && row < m_rows) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < n_valid) dbg_z[static_cast<size_t>(row) * dbg_ld + col0 + j] = __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&bars.tmem_empty[buf]);
+        else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
+      }
+    }
+    const int slot = blockIdx.y * 2 + h;
+    partial[static_cast<size_t>(slot) * m_pad + row] = make_float4(m, s_e, s_ez, s_ezz);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair still uses its smem / barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+size_t fwd_pair_smem_bytes(int d) {
+  return 1024 + static_cast<size_t>(d / kF2BK) * kF2AChunkBytes + kF2Stages * kF2BStageBytes;
+}
+
+int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {
+  const int pairs = (m_rows + 255) / 256;
+  const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
+  const int pair_slots = num_sms / 2;
+  int chunks = (6 * pair_slots + pairs - 1) / pairs;
+  chunks = max(1, min(chunks, max(1, n_tiles / 4)));
+  int tpc = (n_tiles + chunks - 1) / chunks;
+  chunks = (n_tiles + tpc - 1) / tpc;
+  *tiles_per_chunk = tpc;
+  return chunks;
+}
+
+cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
+                                     int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
+                                     float4* partial, float* dbg_z, int dbg_ld, cudaStream_t stream) {
+  const size_t smem = fwd_pair_smem_bytes(d);
+  cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  const int pairs = (m_rows + 255) / 256;
+  const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
+  dim3 grid(2 * pairs, chunks);
+  fwd_rowstats_pair_kernel<<<grid, kF2Threads, smem, stream>>>(tm_rows, tm_cols, m_rows, n_cols, d, n_tiles,
+                                                               tiles_per_chunk, m_pad, scale_log2, partial, dbg_z,
+                                                               dbg_ld);
+  return cudaGetLastError();
+}
+
+}  // namespace scl

@@ -18,9 +18,22 @@ size_t bwd_smem_bytes();
 void bwd_pick_split(int d, int* n_dsplit, int* dn);
 int bwd_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
 cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
-                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                             const float* scale_log2, const float4* row_coef, const float4* col_coef,
                             float* dx_partial, cudaStream_t stream);
+
+// ---- CTA-pair (cta_group::2) variants
+size_t fwd_pair_smem_bytes(int d);
+int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
+cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
+                                     int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
+                                     float4* partial, float* dbg_z, int dbg_ld, cudaStream_t stream);
+size_t bwd_pair_smem_bytes(int d);
+int bwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
+cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+                                 int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
+                                 const float* scale_log2, const float4* row_coef, const float4* col_coef,
+                                 float* dx_partial, cudaStream_t stream);
 
 // ---- HBM-bound side passes (scl_aux.cu)
 cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t,
@@ -40,8 +53,9 @@ cudaError_t launch_loss_scalars(const float* sums6, const float* scalars, float 
                                 cudaStream_t stream);
 cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, const float4* col_stats, int n_cols,
                               int n_pad, int b_local, int rank, const float* gaps, const float* scalars,
-                              const float* grad_out, float c, float w, float mult, int col_mode, float4* row_coef,
-                              float4* col_coef, cudaStream_t stream);
+                              const float* grad_out, float c, float w, float mult, int col_mode, const float* pos_q,
+                              const float* opp_q_local, int kp1, float4* row_coef, float4* col_coef,
+                              cudaStream_t stream);
 cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, int m_rows, int d, const void* y_all,
                               const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
                               const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,

@@ -65,17 +65,20 @@ def _set_ops_for_testing(ops):
 # distributed plumbing (torch.distributed: NCCL on the GPU box, gloo in the CPU tests)
 # ------------------------------------------------------------------------------------------------
 def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
-    """Rank-major concatenation along dim 0 (== torch.cat(all_gather(...)), loss.py:51-57)."""
+    """Rank-major concatenation along dim 0 (== torch.cat(all_gather(...)), loss.py:51-57).
+
+    Moved as raw bytes so that bf16 / int32-bit-pattern payloads work on every backend (gloo has no
+    16-bit integer or bf16 all-gather)."""
     t = t.contiguous()
-    carrier = t.view(torch.int16) if t.dtype in (torch.bfloat16, torch.float16) else t
-    out = torch.empty((world * carrier.shape[0],) + tuple(carrier.shape[1:]), dtype=carrier.dtype, device=t.device)
+    carrier = t.view(torch.uint8).reshape(-1)
+    out = torch.empty(world * carrier.numel(), dtype=torch.uint8, device=t.device)
     try:
         dist.all_gather_into_tensor(out, carrier, group=group)
     except (RuntimeError, NotImplementedError):
         parts = [torch.empty_like(carrier) for _ in range(world)]
         dist.all_gather(parts, carrier, group=group)
         out = torch.cat(parts, dim=0)
-    return out.view(t.dtype) if carrier is not t else out
+    return out.view(t.dtype).reshape((world * t.shape[0],) + tuple(t.shape[1:]))
 
 
 @dataclass
@@ -213,11 +216,13 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if need_i:
             _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
             d_img = ops.bwd_rows(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
-                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0])
+                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0],
+                                 opp_q_local=q_ti)
         if need_t:
             _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
             d_txt = ops.bwd_rows(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
-                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1])
+                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1],
+                                 opp_q_local=q_it)
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)

@@ -101,7 +101,7 @@ class EmulatedOps:
         return torch.stack([loss, gap, ds, 2 * w * gap]).float()
 
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
-                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype):
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
         self.calls.append("bwd_rows")
         m, d = x_rows.shape
         n = y_all.shape[0]

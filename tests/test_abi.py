@@ -36,13 +36,17 @@ def test_every_declared_symbol_is_exported(lib):
 def test_plans_and_errors_without_gpu(lib):
     from spatial_clip_b200._cuda import SclPlan
 
-    assert lib.scl_abi_version() == 1
+    assert lib.scl_abi_version() == 2
     p = SclPlan()
-    assert lib.scl_fwd_plan(4096, 32768, 512, ctypes.byref(p)) == 0
+    assert lib.scl_fwd_plan(4096, 32768, 512, 0, ctypes.byref(p)) == 0
     assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.chunks * p.tiles_per_chunk >= 32768 // 256
-    assert lib.scl_bwd_plan(300, 300, 512, ctypes.byref(p)) == 0
+    assert lib.scl_bwd_plan(300, 300, 512, 0, ctypes.byref(p)) == 0
     assert p.m_pad == 384 and p.n_pad == 384 and p.d_split == 2
-    assert lib.scl_fwd_plan(128, 128, 96, ctypes.byref(p)) == -2  # D % 64 != 0
-    assert lib.scl_fwd_plan(128, 128, 1024, ctypes.byref(p)) == -2  # D > 512 (this round)
+    assert lib.scl_fwd_plan(128, 128, 96, -1, ctypes.byref(p)) == -2  # D % 64 != 0
+    assert lib.scl_fwd_plan(128, 128, 1024, -1, ctypes.byref(p)) == -2  # D > 512 (this round)
     assert b"unsupported shape" in lib.scl_error_string(-2)
+    assert lib.scl_bwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
+    assert p.variant == 1 and p.m_pad == 384 and p.n_pad == 512 and p.d_split == 1
+    assert lib.scl_fwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
+    assert p.variant == 1 and p.m_pad == 512
     assert lib.scl_positives_workspace_bytes(1000) >= 2048 * 12

@@ -15,14 +15,23 @@ LOG2E = 1.4426950408889634
 LN2 = 0.6931471805599453
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=[0, 1], ids=["cta1", "cta2"])
+def ops(request):
+    """CudaOps with the single-CTA (cta_group::1) or CTA-pair (cta_group::2) tensor-core kernels; the
+    modules under test use the same object."""
+    import os
+
     from spatial_clip_b200 import losses
     from spatial_clip_b200._cuda import CudaOps
 
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    losses._set_ops_for_testing(None)
-    return CudaOps()
+    o = CudaOps()
+    o.variant = request.param
+    os.environ["SCL_VARIANT"] = str(request.param)  # inherited by the spawned rank workers
+    prev = losses._set_ops_for_testing(o)
+    yield o
+    losses._set_ops_for_testing(prev)
+    os.environ.pop("SCL_VARIANT", None)
 
 
 def _bf16_pair(m, n, d, seed):
@@ -139,7 +148,7 @@ def test_bwd_rows_matches_dense_formula(ops, m, n, d):
     ld_t = (n + 7) // 8 * 8
     _, y_t = ops.cast_bf16(y, want_rows=False, want_t=True, ld_t=ld_t)
     args = (rs, cs, col, q, ocol, oq, max(m, n), 0, gaps, scal, go, 0.5 / m, 0.05, 1.0, 2, torch.float32)
-    got = ops.bwd_rows(x, y, y_t, *args)
+    got = ops.bwd_rows(x, y, y_t, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
     torch.cuda.synchronize()
     cpu = [a.cpu() if torch.is_tensor(a) else a for a in args]
     want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), y_t.cpu(), *cpu)
