@@ -59,7 +59,7 @@ int num_sms_or_default() {
   return sms;
 }
 
-constexpr int kDefaultVariant = 0;
+constexpr int kDefaultVariant = 1;
 int resolve_variant(int variant) {
   if (variant == 0 || variant == 1) return variant;
   const char* e = std::getenv("SCL_VARIANT");
