@@ -48,7 +48,7 @@ int scl_check_device(int* num_sms);
 typedef struct scl_plan {
   int chunks;          /* column chunks (grid.y for fwd, grid.z for bwd)            */
   int tiles_per_chunk; /* column tiles per chunk                                    */
-  int n_slots;         /* fwd: partial-statistics slots per row (= 2 * chunks)      */
+  int n_slots;         /* fwd: partial-statistics slots per row (2 or 4 per chunk)  */
   int m_pad;           /* rows padded to the 128-row MMA tile                       */
   int n_pad;           /* columns padded to the column tile                         */
   int d_split;         /* bwd: number of D slices (1 or 2; always 1 for the CTA-pair kernel) */

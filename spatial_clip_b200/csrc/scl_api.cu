@@ -114,7 +114,7 @@ int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
     plan->m_pad = (m_rows + 127) / 128 * 128;
   }
   plan->tiles_per_chunk = tpc;
-  plan->n_slots = 2 * plan->chunks;
+  plan->n_slots = (plan->variant == 1 ? 4 : 2) * plan->chunks;
   plan->n_pad = (n_cols + 255) / 256 * 256;
   plan->d_split = 1;
   return SCL_OK;

@@ -23,12 +23,14 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-constexpr int kB2Stages = 6;
+constexpr int kB2Stages = 5;
 constexpr int kB2StageBytes = 16384;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
 constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
 constexpr int kB2GBytes = 4 * kB2GSubBytes;           // 32 KB per buffer
-constexpr int kB2Threads = 384;
+constexpr int kB2EpiWarps = 16;
+constexpr int kB2Threads = (4 + kB2EpiWarps) * 32;  // 640
+constexpr int kB2CoefBytes = kB2TileN * 16;           // 4 KB: float4 per column of the step
 constexpr int kB2ZCol = 256;
 
 struct B2Bars {
@@ -40,6 +42,8 @@ struct B2Bars {
   uint64_t g_full[2];
   uint64_t g_empty[2];
   uint64_t acc_full;
+  uint64_t coef_full[2];
+  uint64_t coef_empty[2];
   uint32_t tmem_base;
 };
 
@@ -56,7 +60,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   const int nk = d / kB2BK;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
   uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 2 x 32 KB
-  uint8_t* smem_ring = smem_g + 2 * kB2GBytes;           // 6 x 16 KB
+  uint8_t* smem_ring = smem_g + 2 * kB2GBytes;           // 5 x 16 KB
+  uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (d + 255) / 256;  // accumulator groups of up to 256 output columns
   const int warp = threadIdx.x >> 5;
@@ -80,9 +85,11 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars.tmem_full[b], 1);
-      mbar_init(&bars.tmem_empty[b], 16);
-      mbar_init(&bars.g_full[b], 16);
+      mbar_init(&bars.tmem_empty[b], 2 * kB2EpiWarps);
+      mbar_init(&bars.g_full[b], 2 * kB2EpiWarps);
       mbar_init(&bars.g_empty[b], 1);
+      mbar_init(&bars.coef_full[b], 1);
+      mbar_init(&bars.coef_empty[b], kB2EpiWarps);
     }
     mbar_init(&bars.acc_full, 1);
     fence_mbar_init();
@@ -111,6 +118,12 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         return s;
       };
       auto push_z = [&](int lt) {
+        // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
+        const int cb = lt & 1;
+        mbar_wait(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.coef_full[cb], kB2CoefBytes);
+        bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
+                     kB2CoefBytes, &bars.coef_full[cb]);
         const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
         for (int kc = 0; kc < nk; ++kc) {
           const int s = acquire();
@@ -189,58 +202,69 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: z -> G (bf16, swizzled smem)
-    const int q = warp & 3;          // TMEM lane quadrant
-    const int h = (warp - 4) >> 2;   // which 64 of this quadrant's 128 columns
-    const int r_loc = (q & 1) * 32 + lane;  // row within this CTA's 64 (2x2 layout: lanes 64.. = upper N half)
+    // 16 warps; each owns one 32-column chunk of the step: TMEM lane quadrant q = warp % 4 (2x2 layout:
+    // lanes 64..127 hold the upper 128 columns), chunk hh = (warp - 4) / 4 of that half's 128 columns.
+    const int q = warp & 3;
+    const int hh = (warp - 4) >> 2;
+    const int r_loc = (q & 1) * 32 + lane;  // row within this CTA's 64
     const int n_half = q >> 1;
-    const int js = n_half * 2 + h;   // 64-column G sub-tile this warp produces
+    const int col_in_step = n_half * 128 + hh * 32;  // first of this warp's 32 columns within the 256-wide step
+    const int js = col_in_step >> 6;                 // 64-column G sub-tile
+    const int c16 = (col_in_step & 63) >> 3;         // first 16-byte chunk inside the sub-tile row (0 or 4)
     const float s2 = __ldg(scale_log2_ptr);
     const float4 rc = __ldg(&row_coef[row0 + r_loc]);  // {Lr, u, v, own-column soft-target term}
+    const float neg_lr = -rc.x;
     const int diag_col = diag0 + row0 + r_loc;
     const int warp_diag_lo = diag0 + row0 + (q & 1) * 32;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
-      mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
-      mbar_wait(&bars.g_empty[buf], ((lt >> 1) & 1) ^ 1);
+      const uint32_t par = (lt >> 1) & 1;
+      mbar_wait(&bars.coef_full[buf], par);
+      mbar_wait(&bars.tmem_full[buf], par);
       tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + hh * 32, r);
+      const float4* cf = reinterpret_cast<const float4*>(smem_coef + buf * kB2CoefBytes) + col_in_step;
+      const int col0 = (t_begin + lt) * kB2TileN + col_in_step;
+      const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
+      const bool ragged = col0 + 32 > n_cols;                                           // warp-uniform
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float g2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float z = __uint_as_float(r[j + e]);
+          const float4 cc = cf[j + e];  // smem broadcast (same address across the warp)
+          const float p = ex2_approx(fmaf(z, s2, neg_lr));
+          const float pc = ex2_approx(fmaf(z, s2, -cc.x));
+          g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
+        }
+        if (has_diag) {
+          const int di = diag_col - col0;
+          g2[0] -= (j == di) ? rc.w : 0.f;
+          g2[1] -= (j + 1 == di) ? rc.w : 0.f;
+        }
+        if (ragged) {
+          g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
+          g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
+        }
+        packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
+      }
+      mbar_wait(&bars.g_empty[buf], par ^ 1);  // the previous user of this G buffer has been consumed
       uint8_t* g_row = smem_g + buf * kB2GBytes + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = (t_begin + lt) * kB2TileN + js * 64 + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + h * 64 + c * 32, r);
-        tmem_ld_wait();
-        uint32_t packed[16];
-        const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
-        const int di = has_diag ? diag_col - col0 : -1;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float g2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float z = __uint_as_float(r[j + e]);
-            const float4 cc = __ldg(&col_coef[col0 + j + e]);  // warp-uniform address
-            const float y = z * s2;
-            const float p = ex2_approx(y - rc.x);
-            const float pc = ex2_approx(y - cc.x);
-            float g = p * fmaf(rc.z, z, rc.y);
-            g = fmaf(pc, fmaf(cc.z, z, cc.y), g);
-            if (has_diag) g -= (j + e == di) ? rc.w : 0.f;
-            g2[e] = (col0 + j + e < n_cols) ? g : 0.f;
-          }
-          packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = (c * 4 + ch) ^ (r_loc & 7);
-          *reinterpret_cast<uint4*>(g_row + chunk * 16) =
-              make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
+        *reinterpret_cast<uint4*>(g_row + chunk * 16) =
+            make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        mbar_arrive(&bars.coef_empty[buf]);
         if (leader) {
           mbar_arrive(&bars.tmem_empty[buf]);
           mbar_arrive(&bars.g_full[buf]);
@@ -250,20 +274,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
       }
     }
-    // ---- drain this CTA's 64-row slice of the dX accumulators
+    // ---- drain this CTA's 64-row slice of the dX accumulators (warp hh takes chunk hh of each group)
     mbar_wait(&bars.acc_full, 0);
     tc_fence_after();
     float* out_row = dx_partial + (static_cast<size_t>(blockIdx.y) * m_pad + row0 + r_loc) * d;
     for (int g = 0; g < ng; ++g) {
       const int n_g = min(256, d - 256 * g);
-      const int n_ch = n_g / 64;  // 32-column chunks in this lane half's n_g / 2 columns
-      const int c_begin = h == 0 ? 0 : n_ch / 2;
-      const int c_end = h == 0 ? n_ch / 2 : n_ch;
-      for (int c = c_begin; c < c_end; ++c) {
+      if (hh * 32 < n_g / 2) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + c * 32, r);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + hh * 32, r);
         tmem_ld_wait();
-        float* dst = out_row + 256 * g + n_half * (n_g / 2) + c * 32;
+        float* dst = out_row + 256 * g + n_half * (n_g / 2) + hh * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -280,7 +301,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
 }
 
 size_t bwd_pair_smem_bytes(int d) {
-  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + 2 * kB2GBytes + kB2Stages * kB2StageBytes;
+  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + 2 * kB2GBytes + kB2Stages * kB2StageBytes +
+         2 * kB2CoefBytes;
 }
 
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {

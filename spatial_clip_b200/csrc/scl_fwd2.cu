@@ -21,7 +21,8 @@ constexpr int kF2Rows = 128;        // rows per CTA (256 per pair)
 constexpr int kF2TileN = 256;       // columns per tile (128 loaded by each CTA)
 constexpr int kF2BK = 64;
 constexpr int kF2Stages = 6;
-constexpr int kF2Threads = 384;
+constexpr int kF2EpiWarps = 16;
+constexpr int kF2Threads = (4 + kF2EpiWarps) * 32;  // 640
 constexpr int kF2AChunkBytes = kF2Rows * kF2BK * 2;  // 16 KB
 constexpr int kF2BStageBytes = 128 * kF2BK * 2;      // 16 KB (this CTA's half of the tile)
 
@@ -66,7 +67,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars.tmem_full[b], 1);
-      mbar_init(&bars.tmem_empty[b], 16);
+      mbar_init(&bars.tmem_empty[b], 2 * kF2EpiWarps);
     }
     fence_mbar_init();
   }
@@ -125,8 +126,10 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
+    // 16 warps: TMEM lane quadrant q = warp % 4, 64-column slice hh = (warp - 4) / 4 of the 256-wide tile.
+    // Thread = row: running max m (log2 units) and the three sums stay in registers for the whole chunk.
     const int q = warp & 3;
-    const int h = (warp - 4) >> 2;
+    const int hh = (warp - 4) >> 2;
     const int row = row0 + q * 32 + lane;
     const float s2 = __ldg(scale_log2_ptr);
     float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
@@ -134,39 +137,77 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
       const int buf = lt & 1;
       mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
       tc_fence_after();
-      const int tile_col0 = (t_begin + lt) * kF2TileN + h * 128;
+      const int tile_col0 = (t_begin + lt) * kF2TileN + hh * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         const int col0 = tile_col0 + c * 32;
         if (col0 >= n_cols) break;  // warp-uniform
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kF2TileN + h * 128 + c * 32, r);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kF2TileN + hh * 64 + c * 32, r);
         tmem_ld_wait();
-        const int n_valid = min(32, n_cols - col0);
-        float y[32];
-        float cm = -INFINITY;
+        if (col0 + 32 <= n_cols && s2 > 0.f) {
+          // ---- fast path (every full tile): no masks, max over the raw similarities, fused scale-and-shift
+          float cm0 = __uint_as_float(r[0]), cm1 = __uint_as_float(r[1]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(r[j]);
-          y[j] = (j < n_valid) ? x * s2 : -INFINITY;
-          cm = fmaxf(cm, y[j]);
-        }
-        const float m_new = fmaxf(m, cm);
-        const float sc = ex2_approx(m - m_new);
-        s_e *= sc;
-        s_ez *= sc;
-        s_ezz *= sc;
-        m = m_new;
+          for (int j = 2; j < 32; j += 2) {
+            cm0 = fmaxf(cm0, __uint_as_float(r[j]));
+            cm1 = fmaxf(cm1, __uint_as_float(r[j + 1]));
+          }
+          const float m_new = fmaxf(m, fmaxf(cm0, cm1) * s2);
+          if (m_new > m) {  // rare after the first few chunks
+            const float sc = ex2_approx(m - m_new);
+            s_e *= sc;
+            s_ez *= sc;
+            s_ezz *= sc;
+            m = m_new;
+          }
+          const float neg_m = -m;
+          float e0 = 0.f, e1 = 0.f, z0 = 0.f, z1 = 0.f, w0 = 0.f, w1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(r[j]);
-          const float e = ex2_approx(y[j] - m);
-          s_e += e;
-          const float t = e * x;
-          s_ez += t;
-          s_ezz = fmaf(t, x, s_ezz);
+          for (int j = 0; j < 32; j += 2) {
+            const float xa = __uint_as_float(r[j]), xb = __uint_as_float(r[j + 1]);
+            const float ea = ex2_approx(fmaf(xa, s2, neg_m));
+            const float eb = ex2_approx(fmaf(xb, s2, neg_m));
+            e0 += ea;
+            e1 += eb;
+            const float ta = ea * xa, tb = eb * xb;
+            z0 += ta;
+            z1 += tb;
+            w0 = fmaf(ta, xa, w0);
+            w1 = fmaf(tb, xb, w1);
+          }
+          s_e += e0 + e1;
+          s_ez += z0 + z1;
+          s_ezz += w0 + w1;
+        } else {
+          // ---- general path: ragged last tile (masked columns) or non-positive scale
+          const int n_valid = min(32, n_cols - col0);
+          float y[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(r[j]);
+            y[j] = (j < n_valid) ? x * s2 : -INFINITY;
+            cm = fmaxf(cm, y[j]);
+          }
+          const float m_new = fmaxf(m, cm);
+          const float sc = ex2_approx(m - m_new);
+          s_e *= sc;
+          s_ez *= sc;
+          s_ezz *= sc;
+          m = m_new;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(r[j]);
+            const float e = ex2_approx(y[j] - m);
+            s_e += e;
+            const float t = e * x;
+            s_ez += t;
+            s_ezz = fmaf(t, x, s_ezz);
+          }
         }
         if (dbg_z != nullptr && row < m_rows) {
+          const int n_valid = min(32, n_cols - col0);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < n_valid) dbg_z[static_cast<size_t>(row) * dbg_ld + col0 + j] = __uint_as_float(r[j]);
@@ -179,7 +220,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
       }
     }
-    const int slot = blockIdx.y * 2 + h;
+    const int slot = blockIdx.y * 4 + hh;
     partial[static_cast<size_t>(slot) * m_pad + row] = make_float4(m, s_e, s_ez, s_ezz);
   }
 

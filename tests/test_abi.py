@@ -39,7 +39,7 @@ def test_plans_and_errors_without_gpu(lib):
     assert lib.scl_abi_version() == 2
     p = SclPlan()
     assert lib.scl_fwd_plan(4096, 32768, 512, 0, ctypes.byref(p)) == 0
-    assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.chunks * p.tiles_per_chunk >= 32768 // 256
+    assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.variant == 0 and p.chunks * p.tiles_per_chunk >= 32768 // 256
     assert lib.scl_bwd_plan(300, 300, 512, 0, ctypes.byref(p)) == 0
     assert p.m_pad == 384 and p.n_pad == 384 and p.d_split == 2
     assert lib.scl_fwd_plan(128, 128, 96, -1, ctypes.byref(p)) == -2  # D % 64 != 0
