@@ -81,9 +81,11 @@ int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr
 /* ---- fused similarity GEMM + online row log-sum-exp (tcgen05) ------------------------------------
  * x_rows[m_rows,d] x y_cols[n_cols,d]^T, both bf16. partial is float4[plan.n_slots * plan.m_pad].
  * Replaces matmul + logit_scale multiply + log_softmax/softmax passes: losses.py:78-89,113-121,
- * loss.py:117-124,150-153.  dbg_z (optional, float[m_rows, dbg_ld]) receives the raw similarities. */
+ * loss.py:117-124,150-153.  dbg_z (optional, float[m_rows, dbg_ld]) receives the raw similarities;
+ * dbg_cycles (optional, 16 int64 per CTA, CTA-pair variant only) receives per-role wait-cycle counters. */
 int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
-                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, void* stream);
+                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, long long* dbg_cycles,
+                     void* stream);
 
 /* merge partials and add the positive logits: row_stats[i] = {LSE_i/ln2, E_p[z], Var_p[z], sum_k q_k z_ik} */
 int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int d, const void* x_rows,
@@ -110,7 +112,7 @@ int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int
  * (rank * b_local, the ground-truth offset of losses.py:94 / loss.py:95-96) */
 int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
                  int d, int diag_col0, const float* scalars3, const scl_plan* plan, const void* row_coef,
-                 const void* col_coef, float* dx_partial, void* stream);
+                 const void* col_coef, float* dx_partial, long long* dbg_cycles, void* stream);
 /* sum the chunk partials, add the neighbour (slot >= 1) soft-target terms, cast: dx_out[m_rows, d] in out_dtype
  * (dx32 is an fp32 work buffer [m_rows, d]; may alias dx_out when out_dtype == 0) */
 int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, int d, const void* y_all,

@@ -40,7 +40,7 @@ EXPORTS = {
                                       C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
     "scl_fwd_rowstats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                   C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+                                   C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "scl_row_finalize": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "scl_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -49,7 +49,8 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                               C.c_void_p, C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                               C.c_void_p, C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
     "scl_bwd_finish": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
@@ -97,6 +98,14 @@ class CudaOps:
         self.variant = -1  # -1: library default (env SCL_VARIANT), 0: single-CTA kernels, 1: CTA-pair kernels
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
+
+    def _cycles(self, name, plan, like):
+        """Developer timing mode: a zeroed int64 buffer (16 counters per CTA) when self.cycle_buffers is a dict."""
+        if getattr(self, "cycle_buffers", None) is None or plan.variant != 1:
+            return None
+        buf = torch.zeros(16 * 4096 * 8, dtype=torch.int64, device=like.device)
+        self.cycle_buffers.setdefault(name, []).append(buf)
+        return buf
 
     def _timed(self, name, device, fn):
         """Run one C-ABI launch, optionally bracketed by CUDA events on its stream (bench.py roofline)."""
@@ -197,7 +206,8 @@ class CudaOps:
         dbg = torch.zeros((m, n), dtype=torch.float32, device=x_rows.device) if debug_z else None
         with torch.cuda.device(x_rows.device):
             self._check(self._timed("fwd_rowstats", x_rows.device, lambda: self.lib.scl_fwd_rowstats(
-                _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n, st)),
+                _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n,
+                _ptr(self._cycles("fwd", plan, x_rows)), st)),
                 "scl_fwd_rowstats")
         self.launches += 1
         return (partial, plan, dbg) if debug_z else (partial, plan)
@@ -254,7 +264,8 @@ class CudaOps:
             self._check(self._timed("bwd_rows", x_rows.device, lambda: self.lib.scl_bwd_rows(
                 _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d, rank * b_local, _ptr(scalars),
                 C.byref(plan),
-                _ptr(row_coef), _ptr(col_coef), _ptr(partial), st)), "scl_bwd_rows")
+                _ptr(row_coef), _ptr(col_coef), _ptr(partial), _ptr(self._cycles("bwd", plan, x_rows)), st)),
+                "scl_bwd_rows")
             self._check(self.lib.scl_bwd_finish(_ptr(partial), C.byref(plan), m, d, _ptr(y_all), _ptr(pos_col),
                                                 _ptr(pos_q), pos_col.shape[1], _ptr(opp_col_all), _ptr(opp_q_all), n,
                                                 b_local, rank, _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c),

@@ -171,7 +171,8 @@ int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr
 }
 
 int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
-                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, void* stream) {
+                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, long long* dbg_cycles,
+                     void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr)
     return SCL_ERR_INVALID_ARG;
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
@@ -183,7 +184,7 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
   if (plan->variant == 1)
     return cuda_rc(scl::launch_fwd_rowstats_pair(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks,
                                                  plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
-                                                 static_cast<float4*>(partial), dbg_z, dbg_ld,
+                                                 static_cast<float4*>(partial), dbg_z, dbg_ld, dbg_cycles,
                                                  static_cast<cudaStream_t>(stream)));
   return cuda_rc(scl::launch_fwd_rowstats(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks, plan->tiles_per_chunk,
                                           plan->m_pad, scalars3 + 1, static_cast<float4*>(partial), dbg_z, dbg_ld,
@@ -231,7 +232,7 @@ int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int
 
 int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
                  int d, int diag_col0, const float* scalars3, const scl_plan* plan, const void* row_coef,
-                 const void* col_coef, float* dx_partial, void* stream) {
+                 const void* col_coef, float* dx_partial, long long* dbg_cycles, void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || y_cols_t == nullptr || scalars3 == nullptr || plan == nullptr ||
       row_coef == nullptr || col_coef == nullptr || dx_partial == nullptr || ld_t < n_cols)
     return SCL_ERR_INVALID_ARG;
@@ -249,7 +250,7 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
     return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
                                              plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
                                              static_cast<const float4*>(row_coef),
-                                             static_cast<const float4*>(col_coef), dx_partial,
+                                             static_cast<const float4*>(col_coef), dx_partial, dbg_cycles,
                                              static_cast<cudaStream_t>(stream)));
   }
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);

@@ -53,9 +53,13 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
                      const __grid_constant__ CUtensorMap tm_cols_t,  // Y^T [D, N]  box {64, 128}
                      int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad, int diag0,
                      const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
-                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial) {
+                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial,
+                     long long* __restrict__ dbg_t) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ B2Bars bars;
+  const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
+  long long* my_t = timed ? dbg_t + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kB2BK;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
@@ -110,9 +114,10 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       for (int kc = 0; kc < nk; ++kc)
         tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
       int it = 0;
+      long long w_empty = 0, w_ce = 0;
       auto acquire = [&]() {
         const int s = it % kB2Stages;
-        mbar_wait(&bars.empty[s], ((it / kB2Stages) & 1) ^ 1);
+        mbar_wait_t(&bars.empty[s], ((it / kB2Stages) & 1) ^ 1, timed, w_empty);
         if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kB2StageBytes);
         ++it;
         return s;
@@ -120,7 +125,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
         const int cb = lt & 1;
-        mbar_wait(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1);
+        mbar_wait_t(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, timed, w_ce);
         mbar_arrive_expect_tx(&bars.coef_full[cb], kB2CoefBytes);
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
@@ -145,22 +150,28 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         if (lt + 1 < n_my) push_z(lt + 1);
         push_yt(lt);
       }
+      if (timed) {
+        my_t[0] = clock64() - t_start;
+        my_t[1] = w_empty;
+        my_t[2] = w_ce;
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
     if (leader && lane == 0) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
-      mbar_wait(&bars.x_full, 0);
+      long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
+      mbar_wait_t(&bars.x_full, 0, timed, w_x);
       tc_fence_after();
       int it = 0;
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
-        mbar_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+        mbar_wait_t(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kB2Stages;
-          mbar_wait(&bars.full[s], (it / kB2Stages) & 1);
+          mbar_wait_t(&bars.full[s], (it / kB2Stages) & 1, timed, w_fz);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_x + kc * kB2XChunkBytes);
           const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes);
@@ -174,14 +185,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       };
       auto issue_acc = [&](int lt) {
         const int gbuf = lt & 1;
-        mbar_wait(&bars.g_full[gbuf], (lt >> 1) & 1);
+        mbar_wait_t(&bars.g_full[gbuf], (lt >> 1) & 1, timed, w_gf);
         tc_fence_after();
         for (int js = 0; js < 4; ++js)
           for (int g = 0; g < ng; ++g, ++it) {
             const int n_g = min(256, d - 256 * g);
             const uint32_t idesc_acc = umma_idesc_bf16(128, n_g);
             const int s = it % kB2Stages;
-            mbar_wait(&bars.full[s], (it / kB2Stages) & 1);
+            mbar_wait_t(&bars.full[s], (it / kB2Stages) & 1, timed, w_fy);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_g + gbuf * kB2GBytes + js * kB2GSubBytes);
             const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes);
@@ -199,6 +210,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         issue_acc(lt);
       }
       tc_commit_pair(&bars.acc_full);
+      if (timed) {
+        my_t[3] = clock64() - t_start;
+        my_t[4] = w_x;
+        my_t[5] = w_te;
+        my_t[6] = w_fz;
+        my_t[7] = w_gf;
+        my_t[8] = w_fy;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: z -> G (bf16, swizzled smem)
@@ -216,11 +235,12 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     const float neg_lr = -rc.x;
     const int diag_col = diag0 + row0 + r_loc;
     const int warp_diag_lo = diag0 + row0 + (q & 1) * 32;
+    long long w_cf = 0, w_tf = 0, w_ge = 0;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       const uint32_t par = (lt >> 1) & 1;
-      mbar_wait(&bars.coef_full[buf], par);
-      mbar_wait(&bars.tmem_full[buf], par);
+      mbar_wait_t(&bars.coef_full[buf], par, timed, w_cf);
+      mbar_wait_t(&bars.tmem_full[buf], par, timed, w_tf);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + hh * 32, r);
@@ -252,7 +272,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
         packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
       }
-      mbar_wait(&bars.g_empty[buf], par ^ 1);  // the previous user of this G buffer has been consumed
+      mbar_wait_t(&bars.g_empty[buf], par ^ 1, timed, w_ge);  // previous user of this G buffer consumed
       uint8_t* g_row = smem_g + buf * kB2GBytes + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -273,6 +293,13 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           mbar_arrive_remote(&bars.g_full[buf], 0);
         }
       }
+    }
+    if (timed && warp == 4 && lane == 0) {
+      my_t[9] = clock64() - t_start;
+      my_t[10] = w_cf;
+      my_t[11] = w_tf;
+      my_t[12] = w_ge;
+      my_t[13] = n_my;
     }
     // ---- drain this CTA's 64-row slice of the dX accumulators (warp hh takes chunk hh of each group)
     mbar_wait(&bars.acc_full, 0);
@@ -320,7 +347,7 @@ int bwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chu
 cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, cudaStream_t stream) {
+                                 float* dx_partial, long long* dbg_t, cudaStream_t stream) {
   const size_t smem = bwd_pair_smem_bytes(d);
   cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
@@ -330,7 +357,7 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
   dim3 grid(2 * pairs, chunks);
   bwd_rows_pair_kernel<<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, n_tiles,
                                                            tiles_per_chunk, m_pad, diag0, scale_log2, row_coef,
-                                                           col_coef, dx_partial);
+                                                           col_coef, dx_partial, dbg_t);
   return cudaGetLastError();
 }
 

@@ -40,9 +40,12 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
                          const __grid_constant__ CUtensorMap tm_cols,  // Y [N, D], box {64, 128}
                          int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad,
                          const float* __restrict__ scale_log2_ptr, float4* __restrict__ partial,
-                         float* __restrict__ dbg_z, int dbg_ld) {
+                         float* __restrict__ dbg_z, int dbg_ld, long long* __restrict__ dbg_t) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ F2Bars bars;
+  const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
+  long long* my_t = timed ? dbg_t + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kF2BK;
   uint8_t* smem_a = smem;
@@ -87,31 +90,37 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
       for (int kc = 0; kc < nk; ++kc)
         tma_load_2d_pair(smem_a + kc * kF2AChunkBytes, &tm_rows, &bars.a_full, kc * kF2BK, row0);
       int it = 0;
+      long long w_empty = 0;
       for (int lt = 0; lt < n_my; ++lt) {
         const int col0 = (t_begin + lt) * kF2TileN + static_cast<int>(cta) * 128;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
-          mbar_wait(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1);
+          mbar_wait_t(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1, timed, w_empty);
           if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kF2BStageBytes);
           tma_load_2d_pair(smem_b + s * kF2BStageBytes, &tm_cols, &bars.full[s], kc * kF2BK, col0);
         }
+      }
+      if (timed) {
+        my_t[0] = clock64() - t_start;  // producer lifetime
+        my_t[1] = w_empty;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
-      mbar_wait(&bars.a_full, 0);
+      long long w_a = 0, w_te = 0, w_full = 0;
+      mbar_wait_t(&bars.a_full, 0, timed, w_a);
       tc_fence_after();
       int it = 0;
       for (int lt = 0; lt < n_my; ++lt) {
         const int buf = lt & 1;
-        mbar_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+        mbar_wait_t(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kF2TileN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
-          mbar_wait(&bars.full[s], (it / kF2Stages) & 1);
+          mbar_wait_t(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + kc * kF2AChunkBytes);
           const uint32_t b_addr = smem_u32(smem_b + s * kF2BStageBytes);
@@ -123,6 +132,12 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         }
         tc_commit_pair(&bars.tmem_full[buf]);
       }
+      if (timed) {
+        my_t[2] = clock64() - t_start;  // MMA thread lifetime (issue side)
+        my_t[3] = w_a;
+        my_t[4] = w_te;
+        my_t[5] = w_full;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
@@ -133,9 +148,10 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     const int row = row0 + q * 32 + lane;
     const float s2 = __ldg(scale_log2_ptr);
     float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
+    long long w_tf = 0;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
-      mbar_wait(&bars.tmem_full[buf], (lt >> 1) & 1);
+      mbar_wait_t(&bars.tmem_full[buf], (lt >> 1) & 1, timed, w_tf);
       tc_fence_after();
       const int tile_col0 = (t_begin + lt) * kF2TileN + hh * 64;
 #pragma unroll 1
@@ -220,6 +236,11 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
       }
     }
+    if (timed && warp == 4 && lane == 0) {
+      my_t[6] = clock64() - t_start;  // epilogue warp lifetime
+      my_t[7] = w_tf;
+      my_t[8] = n_my;
+    }
     const int slot = blockIdx.y * 4 + hh;
     partial[static_cast<size_t>(slot) * m_pad + row] = make_float4(m, s_e, s_ez, s_ezz);
   }
@@ -250,7 +271,8 @@ int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chu
 
 cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
                                      int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
-                                     float4* partial, float* dbg_z, int dbg_ld, cudaStream_t stream) {
+                                     float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
+                                     cudaStream_t stream) {
   const size_t smem = fwd_pair_smem_bytes(d);
   cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
@@ -260,7 +282,7 @@ cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorM
   dim3 grid(2 * pairs, chunks);
   fwd_rowstats_pair_kernel<<<grid, kF2Threads, smem, stream>>>(tm_rows, tm_cols, m_rows, n_cols, d, n_tiles,
                                                                tiles_per_chunk, m_pad, scale_log2, partial, dbg_z,
-                                                               dbg_ld);
+                                                               dbg_ld, dbg_t);
   return cudaGetLastError();
 }
 
