@@ -22,7 +22,14 @@ constexpr int kF2TileN = 256;       // columns per tile (128 loaded by each CTA)
 constexpr int kF2BK = 64;
 constexpr int kF2Stages = 6;
 constexpr int kF2EpiWarps = 16;
-constexpr int kF2Threads = (4 + kF2EpiWarps) * 32;  // 640
+constexpr int kF2Threads = (kF2EpiWarps + 3) * 32;  // 608
+// Warp roles: 0..15 epilogue, 16 TMA producer, 17 MMA issuer, 18 TMEM allocator.  The single-thread roles get
+// the HIGHEST warp ids on purpose: the SM's warp arbiter favours high warp ids, and the MMA issuer shares its
+// scheduler with four busy epilogue warps -- at a low id it was starved of issue slots (measured: ~130 cycles
+// per tcgen05.mma issue against 65 cycles of execution).
+constexpr int kF2ProducerWarp = kF2EpiWarps;
+constexpr int kF2MmaWarp = kF2EpiWarps + 1;
+constexpr int kF2AllocWarp = kF2EpiWarps + 2;
 constexpr int kF2AChunkBytes = kF2Rows * kF2BK * 2;  // 16 KB
 constexpr int kF2BStageBytes = 128 * kF2BK * 2;      // 16 KB (this CTA's half of the tile)
 
@@ -60,7 +67,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
   const int t_end = min(t_begin + tiles_per_chunk, n_tiles);
   const int n_my = t_end - t_begin;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kF2ProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_rows);
     tma_prefetch_desc(&tm_cols);
     mbar_init(&bars.a_full, 1);
@@ -74,7 +81,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kF2AllocWarp) {
     tmem_alloc_pair(&bars.tmem_base, 512);
     tmem_relinquish_pair();
   }
@@ -83,7 +90,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
-  if (warp == 0) {
+  if (warp == kF2ProducerWarp) {
     // ------------------------------------------------------------ TMA producer (one thread per CTA)
     if (lane == 0) {
       if (leader) mbar_arrive_expect_tx(&bars.a_full, static_cast<uint32_t>(2 * nk * kF2AChunkBytes));
@@ -105,9 +112,11 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         my_t[1] = w_empty;
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
-    if (leader && lane == 0) {
+  } else if (warp == kF2MmaWarp) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp walks the loop converged (all lanes poll the barriers); one elected lane issues the
+    // tcgen05 instructions, so the compiler emits them straight-line instead of per-active-lane loops.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
       long long w_a = 0, w_te = 0, w_full = 0;
       mbar_wait_t(&bars.a_full, 0, timed, w_a);
@@ -122,29 +131,31 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
           const int s = it % kF2Stages;
           mbar_wait_t(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + kc * kF2AChunkBytes);
-          const uint32_t b_addr = smem_u32(smem_b + s * kF2BStageBytes);
+          if (elect_one()) {
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + kc * kF2AChunkBytes));
+            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + s * kF2BStageBytes));
 #pragma unroll
-          for (int k = 0; k < kF2BK / 16; ++k)
-            tc_mma_bf16_pair(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                             idesc, (kc | k) != 0 ? 1u : 0u);
-          tc_commit_pair(&bars.empty[s]);
+            for (int k = 0; k < kF2BK / 16; ++k)  // +32 B per K step == +2 in the descriptor's 16-byte address field
+              tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            tc_commit_pair(&bars.empty[s]);
+            if (kc == nk - 1) tc_commit_pair(&bars.tmem_full[buf]);
+          }
+          __syncwarp();
         }
-        tc_commit_pair(&bars.tmem_full[buf]);
       }
-      if (timed) {
-        my_t[2] = clock64() - t_start;  // MMA thread lifetime (issue side)
+      if (timed && lane == 0) {
+        my_t[2] = clock64() - t_start;  // MMA warp lifetime (issue side)
         my_t[3] = w_a;
         my_t[4] = w_te;
         my_t[5] = w_full;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < kF2EpiWarps) {
     // ------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
     // 16 warps: TMEM lane quadrant q = warp % 4, 64-column slice hh = (warp - 4) / 4 of the 256-wide tile.
     // Thread = row: running max m (log2 units) and the three sums stay in registers for the whole chunk.
     const int q = warp & 3;
-    const int hh = (warp - 4) >> 2;
+    const int hh = warp >> 2;
     const int row = row0 + q * 32 + lane;
     const float s2 = __ldg(scale_log2_ptr);
     float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
@@ -236,7 +247,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
       }
     }
-    if (timed && warp == 4 && lane == 0) {
+    if (timed && warp == 0 && lane == 0) {
       my_t[6] = clock64() - t_start;  // epilogue warp lifetime
       my_t[7] = w_tf;
       my_t[8] = n_my;
@@ -247,7 +258,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
 
   tc_fence_before();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair still uses its smem / barriers
-  if (warp == 2) {
+  if (warp == kF2AllocWarp) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
