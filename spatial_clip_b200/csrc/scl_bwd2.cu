@@ -23,7 +23,7 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-constexpr int kB2Stages = 5;
+constexpr int kB2Stages = 7;
 constexpr int kB2StageBytes = 16384;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
 constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
@@ -46,8 +46,8 @@ struct B2Bars {
   uint64_t empty[kB2Stages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t g_full[2];
-  uint64_t g_empty[2];
+  uint64_t g_full;
+  uint64_t g_empty;
   uint64_t acc_full;
   uint64_t coef_full[2];
   uint64_t coef_empty[2];
@@ -70,8 +70,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kB2BK;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
-  uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 2 x 32 KB
-  uint8_t* smem_ring = smem_g + 2 * kB2GBytes;           // 5 x 16 KB
+  uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 32 KB, single buffer (see g_full / g_empty)
+  uint8_t* smem_ring = smem_g + kB2GBytes;               // 7 x 16 KB
   uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (d + 255) / 256;  // accumulator groups of up to 256 output columns
@@ -97,11 +97,11 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars.tmem_full[b], 1);
       mbar_init(&bars.tmem_empty[b], 2 * kB2EpiWarps);
-      mbar_init(&bars.g_full[b], 2 * kB2EpiWarps);
-      mbar_init(&bars.g_empty[b], 1);
       mbar_init(&bars.coef_full[b], 1);
       mbar_init(&bars.coef_empty[b], kB2EpiWarps);
     }
+    mbar_init(&bars.g_full, 2 * kB2EpiWarps);
+    mbar_init(&bars.g_empty, 1);
     mbar_init(&bars.acc_full, 1);
     fence_mbar_init();
   }
@@ -169,17 +169,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
       long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
-      mbar_wait_t(&bars.x_full, 0, timed, w_x);
+      mbar_wait_warp(&bars.x_full, 0, timed, w_x);
       tc_fence_after();
       int it = 0;
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
-        mbar_wait_t(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
+        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kB2Stages;
-          mbar_wait_t(&bars.full[s], (it / kB2Stages) & 1, timed, w_fz);
+          mbar_wait_warp(&bars.full[s], (it / kB2Stages) & 1, timed, w_fz);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_x + kc * kB2XChunkBytes));
@@ -194,25 +194,24 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
       };
       auto issue_acc = [&](int lt) {
-        const int gbuf = lt & 1;
-        mbar_wait_t(&bars.g_full[gbuf], (lt >> 1) & 1, timed, w_gf);
+        mbar_wait_warp(&bars.g_full, lt & 1, timed, w_gf);
         tc_fence_after();
         for (int js = 0; js < 4; ++js)
           for (int g = 0; g < ng; ++g, ++it) {
             const int n_g = min(256, d - 256 * g);
             const uint32_t idesc_acc = umma_idesc_bf16(128, n_g);
             const int s = it % kB2Stages;
-            mbar_wait_t(&bars.full[s], (it / kB2Stages) & 1, timed, w_fy);
+            mbar_wait_warp(&bars.full[s], (it / kB2Stages) & 1, timed, w_fy);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_g + gbuf * kB2GBytes + js * kB2GSubBytes));
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_g + js * kB2GSubBytes));
               const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_acc,
                                  (lt | js | k) != 0 ? 1u : 0u);
               tc_commit_pair(&bars.empty[s]);
-              if (js == 3 && g == ng - 1) tc_commit_pair(&bars.g_empty[gbuf]);
+              if (js == 3 && g == ng - 1) tc_commit_pair(&bars.g_empty);
             }
             __syncwarp();
           }
@@ -253,8 +252,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       const uint32_t par = (lt >> 1) & 1;
-      mbar_wait_t(&bars.coef_full[buf], par, timed, w_cf);
-      mbar_wait_t(&bars.tmem_full[buf], par, timed, w_tf);
+      mbar_wait_warp(&bars.coef_full[buf], par, timed, w_cf);
+      mbar_wait_warp(&bars.tmem_full[buf], par, timed, w_tf);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + hh * 32, r);
@@ -286,8 +285,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
         packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
       }
-      mbar_wait_t(&bars.g_empty[buf], par ^ 1, timed, w_ge);  // previous user of this G buffer consumed
-      uint8_t* g_row = smem_g + buf * kB2GBytes + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
+      // z is in registers now: hand the TMEM buffer back before the (possibly waiting) G write
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars.coef_empty[buf]);
+        if (leader) mbar_arrive(&bars.tmem_empty[buf]);
+        else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
+      }
+      // single G buffer: the second GEMM of the previous step must have consumed it
+      mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1, timed, w_ge);
+      uint8_t* g_row = smem_g + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
@@ -295,17 +303,10 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
             make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       }
       fence_proxy_async();
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&bars.coef_empty[buf]);
-        if (leader) {
-          mbar_arrive(&bars.tmem_empty[buf]);
-          mbar_arrive(&bars.g_full[buf]);
-        } else {
-          mbar_arrive_remote(&bars.tmem_empty[buf], 0);
-          mbar_arrive_remote(&bars.g_full[buf], 0);
-        }
+        if (leader) mbar_arrive(&bars.g_full);
+        else mbar_arrive_remote(&bars.g_full, 0);
       }
     }
     if (timed && warp == 0 && lane == 0) {
@@ -316,7 +317,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       my_t[13] = n_my;
     }
     // ---- drain this CTA's 64-row slice of the dX accumulators (warp hh takes chunk hh of each group)
-    mbar_wait(&bars.acc_full, 0);
+    { long long unused = 0; mbar_wait_warp(&bars.acc_full, 0, false, unused); }
     tc_fence_after();
     float* out_row = dx_partial + (static_cast<size_t>(blockIdx.y) * m_pad + row0 + r_loc) * d;
     for (int g = 0; g < ng; ++g) {
@@ -342,7 +343,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
 }
 
 size_t bwd_pair_smem_bytes(int d) {
-  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + 2 * kB2GBytes + kB2Stages * kB2StageBytes +
+  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + kB2GBytes + kB2Stages * kB2StageBytes +
          2 * kB2CoefBytes;
 }
 

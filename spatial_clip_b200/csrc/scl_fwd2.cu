@@ -119,17 +119,17 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
       long long w_a = 0, w_te = 0, w_full = 0;
-      mbar_wait_t(&bars.a_full, 0, timed, w_a);
+      mbar_wait_warp(&bars.a_full, 0, timed, w_a);
       tc_fence_after();
       int it = 0;
       for (int lt = 0; lt < n_my; ++lt) {
         const int buf = lt & 1;
-        mbar_wait_t(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
+        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kF2TileN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
-          mbar_wait_t(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
+          mbar_wait_warp(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + kc * kF2AChunkBytes));
@@ -162,7 +162,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     long long w_tf = 0;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
-      mbar_wait_t(&bars.tmem_full[buf], (lt >> 1) & 1, timed, w_tf);
+      mbar_wait_warp(&bars.tmem_full[buf], (lt >> 1) & 1, timed, w_tf);
       tc_fence_after();
       const int tile_col0 = (t_begin + lt) * kF2TileN + hh * 64;
 #pragma unroll 1
