@@ -15,6 +15,8 @@
 // Barriers (same smem offset in both CTAs): x_full, full[s], tmem_empty[b], g_full[b] are waited on by
 // the leader (TMA bytes / remote arrivals from the peer are credited to the leader's copy); empty[s],
 // tmem_full[b], g_empty[b], acc_full are multicast by the leader's tcgen05.commit to both CTAs.
+#include <cstdlib>
+
 #include "scl_kernels.h"
 #include "scl_ptx.cuh"
 
@@ -23,8 +25,9 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-constexpr int kB2Stages = 7;
-constexpr int kB2StageBytes = 16384;
+constexpr int kB2Stages = 3;            // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
+constexpr int kB2SlotBytes = 16384;
+constexpr int kB2StageBytes = 2 * kB2SlotBytes;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
 constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
 constexpr int kB2GBytes = 4 * kB2GSubBytes;           // 32 KB per buffer
@@ -71,7 +74,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   const int nk = d / kB2BK;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
   uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 32 KB, single buffer (see g_full / g_empty)
-  uint8_t* smem_ring = smem_g + kB2GBytes;               // 7 x 16 KB
+  uint8_t* smem_ring = smem_g + kB2GBytes;               // 3 x 32 KB
   uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (d + 255) / 256;  // accumulator groups of up to 256 output columns
@@ -120,13 +123,18 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       if (leader) mbar_arrive_expect_tx(&bars.x_full, static_cast<uint32_t>(2 * nk * kB2XChunkBytes));
       for (int kc = 0; kc < nk; ++kc)
         tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
-      int it = 0;
+      int ring_s = 0;
+      uint32_t ring_ph = 0;
       long long w_empty = 0, w_ce = 0;
-      auto acquire = [&]() {
-        const int s = it % kB2Stages;
-        mbar_wait_t(&bars.empty[s], ((it / kB2Stages) & 1) ^ 1, timed, w_empty);
-        if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kB2StageBytes);
-        ++it;
+      // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
+      auto acquire = [&](int n_boxes) {
+        const int s = ring_s;
+        mbar_wait_t(&bars.empty[s], ring_ph ^ 1, timed, w_empty);
+        if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * n_boxes * kB2SlotBytes));
+        if (++ring_s == kB2Stages) {
+          ring_s = 0;
+          ring_ph ^= 1;
+        }
         return s;
       };
       auto push_z = [&](int lt) {
@@ -137,20 +145,27 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
         const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
-        for (int kc = 0; kc < nk; ++kc) {
-          const int s = acquire();
-          tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+        for (int kc = 0; kc < nk; kc += 2) {
+          const int nb = min(2, nk - kc);
+          const int s = acquire(nb);
+          for (int b = 0; b < nb; ++b)
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
+                             (kc + b) * kB2BK, col0);
         }
       };
       auto push_yt = [&](int lt) {
         const int col0 = (t_begin + lt) * kB2TileN;
-        for (int js = 0; js < 4; ++js)
-          for (int g = 0; g < ng; ++g) {
+        const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
+        for (int u = 0; u < n_units; u += 2) {
+          const int nb = min(2, n_units - u);
+          const int s = acquire(nb);
+          for (int b = 0; b < nb; ++b) {
+            const int js = (u + b) / ng, g = (u + b) % ng;
             const int n_g = min(256, d - 256 * g);
-            const int s = acquire();
-            tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols_t, &bars.full[s], col0 + js * 64,
-                             256 * g + static_cast<int>(cta) * (n_g / 2));
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
+                             col0 + js * 64, 256 * g + static_cast<int>(cta) * (n_g / 2));
           }
+        }
       };
       push_z(0);
       for (int lt = 0; lt < n_my; ++lt) {
@@ -165,30 +180,43 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     }
   } else if (warp == kB2MmaWarp) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
-    // Whole warp converged, one elected lane issues (see scl_fwd2.cu).
+    // Whole warp converged, one elected lane issues (see scl_fwd2.cu).  Each barrier wait releases up to
+    // 8 MMAs (two 16 KB boxes): a wait + commit round trip costs the issuing thread ~250 cycles, which at 4
+    // MMAs of 65 cycles per wait left the tensor pipe under-fed.
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
       long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
       mbar_wait_warp(&bars.x_full, 0, timed, w_x);
       tc_fence_after();
-      int it = 0;
+      int ring_s = 0;
+      uint32_t ring_ph = 0;
+      auto advance = [&]() {
+        if (++ring_s == kB2Stages) {
+          ring_s = 0;
+          ring_ph ^= 1;
+        }
+      };
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
         mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int s = it % kB2Stages;
-          mbar_wait_warp(&bars.full[s], (it / kB2Stages) & 1, timed, w_fz);
+        for (int kc = 0; kc < nk; kc += 2, advance()) {
+          const int nb = min(2, nk - kc);
+          const int s = ring_s;
+          mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fz);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_x + kc * kB2XChunkBytes));
-            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes));
+            for (int b = 0; b < nb; ++b) {
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_x + (kc + b) * kB2XChunkBytes));
+              const uint64_t b_desc =
+                  umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_z, (kc | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_z, (kc | b | k) != 0 ? 1u : 0u);
+            }
             tc_commit_pair(&bars.empty[s]);
-            if (kc == nk - 1) tc_commit_pair(&bars.tmem_full[buf]);
+            if (kc + nb >= nk) tc_commit_pair(&bars.tmem_full[buf]);
           }
           __syncwarp();
         }
@@ -196,25 +224,29 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       auto issue_acc = [&](int lt) {
         mbar_wait_warp(&bars.g_full, lt & 1, timed, w_gf);
         tc_fence_after();
-        for (int js = 0; js < 4; ++js)
-          for (int g = 0; g < ng; ++g, ++it) {
-            const int n_g = min(256, d - 256 * g);
-            const uint32_t idesc_acc = umma_idesc_bf16(128, n_g);
-            const int s = it % kB2Stages;
-            mbar_wait_warp(&bars.full[s], (it / kB2Stages) & 1, timed, w_fy);
-            tc_fence_after();
-            if (elect_one()) {
+        const int n_units = 4 * ng;
+        for (int u = 0; u < n_units; u += 2, advance()) {
+          const int nb = min(2, n_units - u);
+          const int s = ring_s;
+          mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fy);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int b = 0; b < nb; ++b) {
+              const int js = (u + b) / ng, g = (u + b) % ng;
+              const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, d - 256 * g));
               const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_g + js * kB2GSubBytes));
-              const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes));
+              const uint64_t b_desc =
+                  umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_acc,
                                  (lt | js | k) != 0 ? 1u : 0u);
-              tc_commit_pair(&bars.empty[s]);
-              if (js == 3 && g == ng - 1) tc_commit_pair(&bars.g_empty);
             }
-            __syncwarp();
+            tc_commit_pair(&bars.empty[s]);
+            if (u + nb >= n_units) tc_commit_pair(&bars.g_empty);
           }
+          __syncwarp();
+        }
       };
       issue_z(0);
       for (int lt = 0; lt < n_my; ++lt) {

@@ -12,6 +12,8 @@
 //   empty[s]          each CTA's producer waits on its own copy; the leader's tcgen05.commit multicasts
 //   tmem_full[b]      each CTA's epilogue waits on its own copy (multicast commit)
 //   tmem_empty[b]     leader only, 16 arrivals: the 8 epilogue warps of both CTAs (peer arrives remotely)
+#include <cstdlib>
+
 #include "scl_kernels.h"
 #include "scl_ptx.cuh"
 

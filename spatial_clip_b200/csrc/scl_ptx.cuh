@@ -60,17 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Warp-level wait: ONE lane polls the barrier, the rest park at the warp barrier (32 lanes polling the same
-// mbarrier serialise in the SYNCS unit and steal issue slots from the working warps).
+// Warp-level wait: every lane polls (the hardware parks a fully waiting warp), then the warp re-converges.
+// Measured: letting ONE lane poll while 31 sit at the warp barrier is ~2.6x slower for the whole kernel.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if ((threadIdx.x & 31) == 0) {
-    if (timed) {
-      const long long t0 = clock64();
-      mbar_wait(bar, parity);
-      acc += clock64() - t0;
-    } else {
-      mbar_wait(bar, parity);
-    }
+  if (timed) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
   }
   __syncwarp();
 }
