@@ -225,19 +225,41 @@ def run_ours(args):
     ms = float(t.item())
     loss_val = float(loss.detach())
 
-    # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> loss D2H, every step
+    # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> loss D2H, every step.
+    # Double-buffered input pipeline: step i+1's H2D copy is enqueued on a copy stream before step i's loss is
+    # read back, so PCIe overlaps the kernels; every step's inputs are still copied inside the timed region.
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    for _ in range(min(2, args.warmup)):
-        l, _, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
-        float(l.detach().cpu())
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def enqueue_copy():
+        with torch.cuda.stream(copy_stream):
+            bufs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs, ev
+
+    def e2e_loop(n_steps):
+        nxt = enqueue_copy()
+        last = None
+        for i in range(n_steps):
+            bufs, ev = nxt
+            main_stream.wait_event(ev)
+            for t in bufs.values():
+                t.record_stream(main_stream)
+            l, _, _ = step(bufs)
+            if i + 1 < n_steps:
+                nxt = enqueue_copy()
+            last = float(l.detach().to("cpu"))  # D2H read of the step's result (synchronises)
+        return last
+
+    e2e_loop(min(2, max(1, args.warmup)))
     sync_all()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(e2e_steps):
-        l, _, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
-        l.detach().to("cpu", non_blocking=False)
+    e2e_loop(e2e_steps)
     t1.record()
     sync_all()
     te = torch.tensor([t0.elapsed_time(t1) / e2e_steps], device=dev)
@@ -270,10 +292,10 @@ def run_ours(args):
         "pairs_per_s_per_gpu": pairs_per_s / world,
         "loss": loss_val,
         "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "pipeline": "double-buffered H2D on a copy stream, loss read back every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "bwd_rows_kernel", "achieved": achieved, "peak": pk["burst"],
+        "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel" if ops.fwd_plan(256, 256, D).variant == 1 else "bwd_rows_kernel", "achieved": achieved, "peak": pk["burst"],
                      "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": None,
                      "peak_source": pk["source"], "launch_ms": k_ms, "launches_per_step": len(ev) // max(1, args.steps),
                      "algorithmic_flops_per_launch": alg_flops_launch,
@@ -281,7 +303,10 @@ def run_ours(args):
                      "fwd_rowstats_launch_ms": f_ms,
                      "fwd_rowstats_tflops": 2.0 * b_local * N_GLOBAL * D / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
                      "step_algorithmic_tflops_per_gpu": step_alg_tflops,
-                     "step_frac_of_burst": step_alg_tflops / pk["burst"]},
+                     "step_frac_of_burst": step_alg_tflops / pk["burst"],
+                     "executed_tflops": 2.0 * alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
+                     "note": "achieved counts the dX GEMM only (algorithmic); the launch also recomputes the similarity "
+                             "tile once (executed = 2x)"},
         "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"1024 local rows x N={N_GLOBAL} columns (one rank of a W=32 emulation), fwd+bwd, "
                                    f"oracle/torch_port.py (torch CPU fp32), {cpu_sec:.2f} s"},
