@@ -86,6 +86,24 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+class _DeviceGuard:
+    """`with torch.cuda.device(d)` costs ~10 us per use; skip it when d is already the current device (the
+    normal case: DDP ranks, and the autograd engine sets the device on its threads)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 class CudaOps:
     """Tensor-level wrappers over the C ABI.  Every method launches on the current stream of the
     tensors' device and returns without synchronising."""
@@ -162,7 +180,7 @@ class CudaOps:
         if want_t:
             y_t = torch.zeros((d, ld_t), dtype=torch.bfloat16, device=x.device) if ld_t != rows else \
                 self.empty((d, ld_t), torch.bfloat16, x)
-        with torch.cuda.device(x.device):
+        with _DeviceGuard(x.device):
             self._check(self.lib.scl_cast_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(y), _ptr(y_t), rows, d, ld_t,
                                                int(normalize), st), "scl_cast_bf16")
         self.launches += 1
@@ -171,7 +189,7 @@ class CudaOps:
     def prep_scalars(self, logit_scale, cap):
         st = self._stream(logit_scale)
         out = self.empty((3,), torch.float32, logit_scale)
-        with torch.cuda.device(logit_scale.device):
+        with _DeviceGuard(logit_scale.device):
             self._check(self.lib.scl_prep_scalars(_ptr(logit_scale), float(cap) if cap is not None else -1.0,
                                                   _ptr(out), st), "scl_prep_scalars")
         self.launches += 1
@@ -189,7 +207,7 @@ class CudaOps:
         if k > 0:
             ws_bytes = self.lib.scl_positives_workspace_bytes(n_global)
             ws = self.empty((ws_bytes,), torch.uint8, like)
-        with torch.cuda.device(like.device):
+        with _DeviceGuard(like.device):
             self._check(self.lib.scl_build_positives(_ptr(all_ids), max(n_global, b_local), _ptr(nbr_ids),
                                                      _ptr(nbr_alpha), b_local, k, float(alpha_scale), rank, _ptr(ws),
                                                      ws_bytes, _ptr(col), _ptr(w), _ptr(q), st),
@@ -204,7 +222,7 @@ class CudaOps:
         plan = self.fwd_plan(m, n, d)
         partial = self.empty((plan.n_slots * plan.m_pad, 4), torch.float32, x_rows)
         dbg = torch.zeros((m, n), dtype=torch.float32, device=x_rows.device) if debug_z else None
-        with torch.cuda.device(x_rows.device):
+        with _DeviceGuard(x_rows.device):
             self._check(self._timed("fwd_rowstats", x_rows.device, lambda: self.lib.scl_fwd_rowstats(
                 _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n,
                 _ptr(self._cycles("fwd", plan, x_rows)), st)),
@@ -216,7 +234,7 @@ class CudaOps:
         st = self._stream(x_rows)
         m, d = x_rows.shape
         stats = self.empty((m, 4), torch.float32, x_rows)
-        with torch.cuda.device(x_rows.device):
+        with _DeviceGuard(x_rows.device):
             self._check(self.lib.scl_row_finalize(_ptr(partial), C.byref(plan), m, d, _ptr(x_rows), _ptr(y_all),
                                                   _ptr(pos_col), _ptr(pos_q), pos_col.shape[1], _ptr(stats), st),
                         "scl_row_finalize")
@@ -226,7 +244,7 @@ class CudaOps:
     def reduce_rows(self, stats_a, stats_b, scalars):
         st = self._stream(stats_a)
         sums = self.empty((6,), torch.float32, stats_a)
-        with torch.cuda.device(stats_a.device):
+        with _DeviceGuard(stats_a.device):
             self._check(self.lib.scl_reduce_rows(_ptr(stats_a), _ptr(stats_b), stats_a.shape[0], _ptr(scalars),
                                                  _ptr(sums), st), "scl_reduce_rows")
         self.launches += 1
@@ -235,7 +253,7 @@ class CudaOps:
     def loss_scalars(self, sums6, scalars, c, w):
         st = self._stream(sums6)
         out = self.empty((4,), torch.float32, sums6)
-        with torch.cuda.device(sums6.device):
+        with _DeviceGuard(sums6.device):
             self._check(self.lib.scl_loss_scalars(_ptr(sums6), _ptr(scalars), float(c), float(w), _ptr(out), st),
                         "scl_loss_scalars")
         self.launches += 1
@@ -255,7 +273,7 @@ class CudaOps:
         out = dx32 if out_dtype == torch.float32 else self.empty((m, d), out_dtype, x_rows)
         if opp_q_local is None:  # single rank: the gathered opposite list IS the local one
             opp_q_local = opp_q_all[rank * b_local:(rank + 1) * b_local]
-        with torch.cuda.device(x_rows.device):
+        with _DeviceGuard(x_rows.device):
             self._check(self.lib.scl_bwd_coeffs(_ptr(row_stats), m, _ptr(col_stats), n, C.byref(plan), b_local, rank,
                                                 _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c), float(w),
                                                 float(mult), col_mode, _ptr(pos_q), _ptr(opp_q_local),

@@ -121,8 +121,14 @@ class _ContrastiveLossFn(torch.autograd.Function):
         scalars = ops.prep_scalars(scale, cfg.cap)
 
         # ---- features: bf16 copies, gathered rank-major (gather_features, loss.py:21-65)
-        img_l, _ = ops.cast_bf16(image_features.detach().contiguous())
-        txt_l, _ = ops.cast_bf16(text_features.detach().contiguous())
+        # single rank + backward wanted: the transposed copies the backward GEMMs need come out of the same
+        # pass over the fp32 inputs (dImage needs text^T, dGene needs image^T)
+        ld_t = (n + 7) // 8 * 8
+        fuse_t = world == 1 and torch.is_grad_enabled()
+        img_l, img_t = ops.cast_bf16(image_features.detach().contiguous(),
+                                     want_t=fuse_t and ctx.needs_input_grad[1], ld_t=ld_t)
+        txt_l, txt_t = ops.cast_bf16(text_features.detach().contiguous(),
+                                     want_t=fuse_t and ctx.needs_input_grad[0], ld_t=ld_t)
         if world > 1:
             img_all = _all_gather_rows(img_l, world, cfg.group)
             txt_all = _all_gather_rows(txt_l, world, cfg.group)
@@ -172,6 +178,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ctx.c = c
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
         ctx.scale_shape = logit_scale.shape
+        ctx.transposed = (img_t, txt_t)  # None unless produced above
         ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
                               q_ti)
         ctx.mark_non_differentiable(col_it, w_it, q_it)
@@ -213,13 +220,16 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ld_t = (n + 7) // 8 * 8
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_scale = None
+        img_all_t, txt_all_t = ctx.transposed
         if need_i:
-            _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
+            if txt_all_t is None:
+                _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
             d_img = ops.bwd_rows(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
                                  b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0],
                                  opp_q_local=q_ti)
         if need_t:
-            _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
+            if img_all_t is None:
+                _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
             d_txt = ops.bwd_rows(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
                                  b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1],
                                  opp_q_local=q_it)
