@@ -124,7 +124,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         # single rank + backward wanted: the transposed copies the backward GEMMs need come out of the same
         # pass over the fp32 inputs (dImage needs text^T, dGene needs image^T)
         ld_t = (n + 7) // 8 * 8
-        fuse_t = world == 1 and torch.is_grad_enabled()
+        fuse_t = world == 1  # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
         img_l, img_t = ops.cast_bf16(image_features.detach().contiguous(),
                                      want_t=fuse_t and ctx.needs_input_grad[1], ld_t=ld_t)
         txt_l, txt_t = ops.cast_bf16(text_features.detach().contiguous(),
