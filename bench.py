@@ -273,6 +273,11 @@ def run_ours(args):
         return
 
     pk = peaks()
+    traffic = None  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (1 GPU)
+    tp = ROOT / "profiles" / "r1_traffic.json"
+    if tp.exists() and world == 1:
+        tj = json.loads(tp.read_text()).get("bwd_rows_pair_kernel", {})
+        traffic = tj.get("dram_bytes_read", 0) + tj.get("dram_bytes_write", 0)
     # dominant kernel: bwd_rows, two launches per step (d image, d gene)
     ev = kernel_events.get("bwd_rows", [])
     k_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
@@ -296,7 +301,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel" if ops.fwd_plan(256, 256, D).variant == 1 else "bwd_rows_kernel", "achieved": achieved, "peak": pk["burst"],
-                     "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": traffic,
                      "peak_source": pk["source"], "launch_ms": k_ms, "launches_per_step": len(ev) // max(1, args.steps),
                      "algorithmic_flops_per_launch": alg_flops_launch,
                      "frac_of_sustained": achieved / pk["sustained"],

@@ -121,6 +121,12 @@ int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, in
                    const float* scalars3, const float* grad_out, float c, float w, float mult, int col_mode,
                    float* dx32, void* dx_out, int out_dtype, void* stream);
 
+/* ---- statistics exchange helper (replaces torch.distributed.nn's reduce-scatter in backward) ----
+ * gathered: float[world][rec_floats], the all-gathered flat per-rank records (host arrays outs/offs/lens of
+ * n_comp <= 8 entries): component k of every rank is copied to outs[k][rank * lens[k] ...], one launch. */
+int scl_unpack_records(const float* gathered, int world, int rec_floats, int n_comp, float* const* outs,
+                       const int* offs, const int* lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

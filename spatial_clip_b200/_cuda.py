@@ -55,6 +55,8 @@ EXPORTS = {
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
+    "scl_unpack_records": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -258,6 +260,30 @@ class CudaOps:
                         "scl_loss_scalars")
         self.launches += 1
         return out
+
+    def exchange_records(self, parts, world, gather_fn):
+        """All-gather a list of per-rank [B_l, k] fp32/int32 tensors as ONE flat record per rank and split the
+        result into contiguous rank-major [world*B_l, k] tensors (one collective + two launches)."""
+        like = parts[0]
+        st = self._stream(like)
+        flat = torch.cat([p.reshape(-1).view(torch.float32) for p in parts])
+        rec = flat.numel()
+        gathered = gather_fn(flat.reshape(1, rec))  # [world, rec]
+        outs = [self.empty((world * p.shape[0],) + tuple(p.shape[1:]), p.dtype, like) for p in parts]
+        n = len(parts)
+        ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        offs = (C.c_int * n)()
+        lens = (C.c_int * n)()
+        o = 0
+        for k, p in enumerate(parts):
+            offs[k] = o
+            lens[k] = p.numel()
+            o += p.numel()
+        with _DeviceGuard(like.device):
+            self._check(self.lib.scl_unpack_records(_ptr(gathered), world, rec, n, ptrs, offs, lens, st),
+                        "scl_unpack_records")
+        self.launches += 2
+        return outs
 
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):

@@ -281,4 +281,12 @@ int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, in
                                         static_cast<cudaStream_t>(stream)));
 }
 
+int scl_unpack_records(const float* gathered, int world, int rec_floats, int n_comp, float* const* outs,
+                       const int* offs, const int* lens, void* stream) {
+  if (gathered == nullptr || outs == nullptr || offs == nullptr || lens == nullptr || world < 1 || rec_floats < 1)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_unpack_records(gathered, world, rec_floats, n_comp, outs, offs, lens,
+                                            static_cast<cudaStream_t>(stream)));
+}
+
 }  // extern "C"

@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
     *reinterpret_cast<float4*>(dx32 + static_cast<size_t>(row) * d + c0) = acc;
   }
 }
-// warp per (global opposite-direction row j, slot t): if that row lists one of OUR rows as a positive,
+// Scan of the gathered opposite-direction lists: lane = one (row j, slot t) entry (coalesced), entries that
+// list one of OUR rows as a positive are then processed by the whole warp, one hit at a time:
 //   dx32[col - rank*B_l, :] -= g*c*(s_eff + k2_owner(j)) * q_jt * Y[j,:]        (fp32 atomics)
 __global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict__ opp_col_all,
                                                           const float* __restrict__ opp_q_all, int n_global, int kp1,
@@ -443,21 +444,40 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict_
                                                           const float* __restrict__ scalars,
                                                           const float* __restrict__ grad_out, float c, float w,
                                                           float mult, int col_mode, float* __restrict__ dx32) {
-  const long long e = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (e >= static_cast<long long>(n_global) * kp1) return;
-  const int j = static_cast<int>(e / kp1);
-  if (e % kp1 == 0) return;  // slot 0 (own column) is handled inside bwd_rows_kernel
-  const int col = opp_col_all[e];
-  if (col < rank * b_local || col >= (rank + 1) * b_local) return;
-  const int owner = j / b_local;
-  if (col_mode == 0 || (col_mode == 1 && owner != rank)) return;
-  const float qc = -grad_out[0] * mult * c * (scalars[0] + 2.f * w * gaps[owner]) * opp_q_all[e];
-  float* dst = dx32 + static_cast<size_t>(col - rank * b_local) * d;
-  for (int c0 = lane * 2; c0 < d; c0 += 64) {
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y_all + static_cast<size_t>(j) * d + c0));
-    atomicAdd(dst + c0, qc * v.x);
-    atomicAdd(dst + c0 + 1, qc * v.y);
+  const long long total = static_cast<long long>(n_global) * kp1;
+  const long long e = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 32 + lane;
+  int col = -1, j = 0;
+  float qv = 0.f;
+  if (e < total) {
+    j = static_cast<int>(e / kp1);
+    const int t = static_cast<int>(e - static_cast<long long>(j) * kp1);
+    const int cc = opp_col_all[e];
+    const int owner = j / b_local;
+    const bool mode_ok = col_mode == 2 || (col_mode == 1 && owner == rank);
+    // slot 0 (own column) is handled inside the tensor-core kernel
+    if (t != 0 && mode_ok && cc >= rank * b_local && cc < (rank + 1) * b_local) {
+      col = cc;
+      qv = opp_q_all[e];
+    }
+  }
+  unsigned hits = __ballot_sync(0xffffffffu, col >= 0);
+  const float base = -grad_out[0] * mult * c;
+  const float s_eff = scalars[0];
+  while (hits) {
+    const int src = __ffs(hits) - 1;
+    hits &= hits - 1;
+    const int hc = __shfl_sync(0xffffffffu, col, src);
+    const int hj = __shfl_sync(0xffffffffu, j, src);
+    const float hq = __shfl_sync(0xffffffffu, qv, src);
+    const float qc = base * (s_eff + 2.f * w * gaps[hj / b_local]) * hq;
+    float* dst = dx32 + static_cast<size_t>(hc - rank * b_local) * d;
+    const __nv_bfloat16* yrow = y_all + static_cast<size_t>(hj) * d;
+    for (int c0 = lane * 2; c0 < d; c0 += 64) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + c0));
+      atomicAdd(dst + c0, qc * v.x);
+      atomicAdd(dst + c0 + 1, qc * v.y);
+    }
   }
 }
 template <typename T>
@@ -481,7 +501,7 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                                                           kp1, rank, gaps, scalars, grad_out, c, w, mult, dx32);
   if (col_mode != 0) {
     const long long entries = static_cast<long long>(n_global) * kp1;
-    bwd_scatter_kernel<<<static_cast<unsigned>((entries + 7) / 8), 256, 0, stream>>>(
+    bwd_scatter_kernel<<<static_cast<unsigned>((entries + 255) / 256), 256, 0, stream>>>(
         opp_col_all, opp_q_all, n_global, kp1, b_local, rank, d, yb, gaps, scalars, grad_out, c, w, mult, col_mode,
         dx32);
   }
@@ -491,6 +511,49 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
         dx32, static_cast<__nv_bfloat16*>(dx_out), n);
   else if (out_dtype == 2)
     cast_out_kernel<__half><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(dx32, static_cast<__half*>(dx_out), n);
+  return cudaGetLastError();
+}
+
+
+// =====================================================================================
+// statistics exchange: split the all-gathered per-rank records back into contiguous arrays
+// =====================================================================================
+// in: [world][rec_floats] (each rank's flat record); component k of rank r lives at in[r*rec + off[k] .. + len[k])
+// and goes to out[k][r*len[k] ..].  One launch instead of one strided copy per component.
+struct UnpackDesc {
+  float* out[8];
+  int off[8];
+  int len[8];
+  int n;
+};
+__global__ void unpack_records_kernel(const float* __restrict__ in, int world, int rec_floats, UnpackDesc dsc) {
+  const int k = blockIdx.y;
+  if (k >= dsc.n) return;
+  const long long total = static_cast<long long>(world) * dsc.len[k];
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / dsc.len[k]);
+    const int o = static_cast<int>(i - static_cast<long long>(r) * dsc.len[k]);
+    dsc.out[k][i] = in[static_cast<size_t>(r) * rec_floats + dsc.off[k] + o];
+  }
+}
+cudaError_t launch_unpack_records(const float* in, int world, int rec_floats, int n_comp, float* const* outs,
+                                  const int* offs, const int* lens, cudaStream_t stream) {
+  if (n_comp < 1 || n_comp > 8) return cudaErrorInvalidValue;
+  UnpackDesc dsc;
+  dsc.n = n_comp;
+  int max_len = 0;
+  for (int k = 0; k < n_comp; ++k) {
+    dsc.out[k] = outs[k];
+    dsc.off[k] = offs[k];
+    dsc.len[k] = lens[k];
+    max_len = max(max_len, lens[k]);
+  }
+  const long long total = static_cast<long long>(world) * max_len;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  const int bx = static_cast<int>(blocks);
+  unpack_records_kernel<<<dim3(max(bx, 1), n_comp), 256, 0, stream>>>(in, world, rec_floats, dsc);
   return cudaGetLastError();
 }
 

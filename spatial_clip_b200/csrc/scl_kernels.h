@@ -63,4 +63,7 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                               const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
                               float* dx32, void* dx_out, int out_dtype, cudaStream_t stream);
 
+cudaError_t launch_unpack_records(const float* in, int world, int rec_floats, int n_comp, float* const* outs,
+                                  const int* offs, const int* lens, cudaStream_t stream);
+
 }  // namespace scl

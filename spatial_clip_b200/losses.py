@@ -196,18 +196,11 @@ class _ContrastiveLossFn(torch.autograd.Function):
 
         # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients
         if world > 1:
-            kp1 = col_it.shape[1]
-            pack = torch.cat([stats_i, stats_t, col_it.view(torch.float32), q_it, col_ti.view(torch.float32), q_ti,
-                              out4[1:2].expand(b_local, 1)], dim=1).contiguous()
-            allp = _all_gather_rows(pack, world, cfg.group)
-            stats_i_all = allp[:, 0:4].contiguous()
-            stats_t_all = allp[:, 4:8].contiguous()
-            o = 8
-            col_it_all = allp[:, o:o + kp1].contiguous().view(torch.int32)
-            q_it_all = allp[:, o + kp1:o + 2 * kp1].contiguous()
-            col_ti_all = allp[:, o + 2 * kp1:o + 3 * kp1].contiguous().view(torch.int32)
-            q_ti_all = allp[:, o + 3 * kp1:o + 4 * kp1].contiguous()
-            gaps = allp[:, o + 4 * kp1].reshape(world, b_local)[:, 0].contiguous()
+            gap_rows = out4[1:2].reshape(1, 1)
+            (stats_i_all, stats_t_all, col_it_all, q_it_all, col_ti_all, q_ti_all, gaps) = ops.exchange_records(
+                [stats_i, stats_t, col_it, q_it, col_ti, q_ti, gap_rows], world,
+                lambda t: _all_gather_rows(t, world, cfg.group))
+            gaps = gaps.reshape(world)
         else:
             stats_i_all, stats_t_all = stats_i, stats_t
             col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti

@@ -100,6 +100,17 @@ class EmulatedOps:
         ds = gsum + 2 * w * gap * c * (s[4] + s[5])
         return torch.stack([loss, gap, ds, 2 * w * gap]).float()
 
+    def exchange_records(self, parts, world, gather_fn):
+        self.calls.append("exchange_records")
+        flat = torch.cat([p.reshape(-1).view(torch.float32) for p in parts])
+        gathered = gather_fn(flat.reshape(1, -1))
+        outs, o = [], 0
+        for p in parts:
+            n = p.numel()
+            outs.append(gathered[:, o:o + n].contiguous().view(p.dtype).reshape((world * p.shape[0],) + tuple(p.shape[1:])))
+            o += n
+        return outs
+
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
         self.calls.append("bwd_rows")
