@@ -145,7 +145,8 @@ int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
 int scl_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t, int normalize,
                   void* stream) {
   if (x == nullptr || (y == nullptr && y_t == nullptr) || rows < 0 || d <= 0 || d % 64 != 0 || src_dtype < 0 ||
-      src_dtype > 2 || (y_t != nullptr && ld_t < rows))
+      src_dtype > 2 || (y_t != nullptr && ld_t < rows) || (reinterpret_cast<uintptr_t>(x) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(y) & 7) != 0 || (reinterpret_cast<uintptr_t>(y_t) & 15) != 0)
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_cast_bf16(x, src_dtype, y, y_t, rows, d, ld_t, normalize, static_cast<cudaStream_t>(stream)));
 }

@@ -28,52 +28,102 @@ __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat1
 template <>
 __device__ __forceinline__ float load_as_float<__half>(const __half* p, size_t i) { return __half2float(p[i]); }
 
-// One CTA handles a [64 rows x d] slab: optional per-row 1/||x||, bf16 row-major copy, and the transposed
-// copy y_t[d][ld_t] written 64 consecutive rows (=128 B) at a time through a padded smem tile.
+// One CTA handles a [64 rows x d] slab in [64 x 64] tiles: 16-byte global loads (4 fp32 / 8 bf16 per thread),
+// optional per-row 1/||x||, 8-byte row-major bf16 stores, and the transposed copy y_t[d][ld_t] written as
+// 16-byte vectors of 8 consecutive rows assembled from a padded smem tile.
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                         __nv_bfloat16* __restrict__ y_t, int rows, int d, int ld_t,
                                                         int normalize) {
   __shared__ float inv_norm[64];
-  __shared__ __nv_bfloat16 tile[64][66];
+  // [row][col + 8 * (row / 8)]: 240-byte pitch plus a per-8-row-group skew makes the 8-row column gathers of the
+  // transposed store hit 8 different banks
+  __shared__ __nv_bfloat16 tile[64][120];
   const int r0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = warp; rr < 64; rr += 8) {
-    float inv = 1.f;
-    const int r = r0 + rr;
-    if (normalize && r < rows) {
+  if (normalize) {
+    for (int rr = warp; rr < 64; rr += 8) {
+      const int r = r0 + rr;
       float ss = 0.f;
-      for (int c = lane; c < d; c += 32) {
-        const float v = load_as_float(x, static_cast<size_t>(r) * d + c);
-        ss = fmaf(v, v, ss);
+      if (r < rows) {
+        for (int c = lane * 4; c < d; c += 128) {
+          float v[4];
+          load4(x + static_cast<size_t>(r) * d + c, v);
+          ss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], ss))));
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (open_clip model.py:328,345)
+      if (lane == 0) inv_norm[rr] = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (open_clip model.py:328,345)
     }
-    if (lane == 0) inv_norm[rr] = inv;
+  } else if (threadIdx.x < 64) {
+    inv_norm[threadIdx.x] = 1.f;
   }
   __syncthreads();
+  // thread -> (row rr = tid / 16 + 16 * pass, 4 columns at 4 * (tid % 16))
+  const int tc = (threadIdx.x & 15) * 4;
+  const int tr = threadIdx.x >> 4;
+  // transposed stores: thread -> (column cc = tid / 8 + 32 * pass, 8 rows at 8 * (tid % 8))
+  const int sr = (threadIdx.x & 7) * 8;
+  const int sc = threadIdx.x >> 3;
+  const bool full_rows = r0 + 64 <= rows && (ld_t % 8) == 0;
   for (int c0 = 0; c0 < d; c0 += 64) {
-    // 64 x 64 tile: thread (ty = tid/64 .. , tx = tid%64)
-    for (int rr = threadIdx.x >> 6; rr < 64; rr += 4) {
-      const int cc = threadIdx.x & 63;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int rr = tr + 16 * pass;
       const int r = r0 + rr;
-      float v = 0.f;
-      if (r < rows) v = load_as_float(x, static_cast<size_t>(r) * d + c0 + cc) * inv_norm[rr];
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
-      tile[rr][cc] = b;
-      if (y != nullptr && r < rows) y[static_cast<size_t>(r) * d + c0 + cc] = b;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < rows) load4(x + static_cast<size_t>(r) * d + c0 + tc, v);
+      const float s = inv_norm[rr];
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0] * s, v[1] * s);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2] * s, v[3] * s);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(&tile[rr][tc + 8 * (rr >> 3)]) = packed;
+      if (y != nullptr && r < rows) *reinterpret_cast<uint2*>(y + static_cast<size_t>(r) * d + c0 + tc) = packed;
     }
-    __syncthreads();
     if (y_t != nullptr) {
-      for (int cc = threadIdx.x >> 6; cc < 64; cc += 4) {
-        const int rr = threadIdx.x & 63;
-        const int r = r0 + rr;
-        if (r < rows) y_t[static_cast<size_t>(c0 + cc) * ld_t + r] = tile[rr][cc];
+      __syncthreads();
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int cc = sc + 32 * pass;
+        __nv_bfloat16 col[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) col[k] = tile[sr + k][cc + sr];
+        __nv_bfloat16* dst = y_t + static_cast<size_t>(c0 + cc) * ld_t + r0 + sr;
+        if (full_rows) {
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(col);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (r0 + sr + k < rows) dst[k] = col[k];
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
