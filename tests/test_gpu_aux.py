@@ -31,6 +31,6 @@ def test_normalize_matches_f_normalize(ops):
     y, _ = ops.cast_bf16(x, normalize=True)
     want = torch.nn.functional.normalize(x, dim=-1)
     # reference: open_clip model.py:326-345 normalises in fp32; we round the result to bf16
-    assert (y.float() - want).abs().max().item() <= 2 ** -9 * want.abs().max().item() + 1e-6
+    assert (y.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6  # bf16 half-ulp
     norms = y.float().norm(dim=-1)
     assert (norms - 1).abs().max().item() < 5e-3
