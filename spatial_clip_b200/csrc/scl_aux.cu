@@ -311,16 +311,22 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restr
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= m_rows) return;
+  // lanes split the slots; the merge is a max-rescaled sum, combined across lanes in a fixed butterfly order
   float m = -INFINITY;
-  for (int s = 0; s < n_slots; ++s) m = fmaxf(m, partial[static_cast<size_t>(s) * m_pad + row].x);
+  for (int s = lane; s < n_slots; s += 32) m = fmaxf(m, partial[static_cast<size_t>(s) * m_pad + row].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  for (int s = 0; s < n_slots; ++s) {  // fixed order -> deterministic
+  for (int s = lane; s < n_slots; s += 32) {
     const float4 p = partial[static_cast<size_t>(s) * m_pad + row];
     const float w = (p.x == -INFINITY) ? 0.f : exp2f(p.x - m);
     s0 = fmaf(p.y, w, s0);
     s1 = fmaf(p.z, w, s1);
     s2 = fmaf(p.w, w, s2);
   }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
   const float mu = s1 / s0;
   const float var = s2 / s0 - mu * mu;
   float zq = 0.f;

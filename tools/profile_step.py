@@ -52,6 +52,22 @@ for _ in range(n_steps):
     step()
 cpu_ms = (time.perf_counter() - t0) * 1e3 / n_steps
 torch.cuda.synchronize()
+if os.environ.get("SCL_CPROFILE") and rank == 0:
+    import cProfile
+    import pstats
+
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20):
+        step()
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr)
+    st.sort_stats("tottime").print_stats(28)
+elif os.environ.get("SCL_CPROFILE"):
+    for _ in range(20):
+        step()
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(n_steps):
         step()
