@@ -19,7 +19,8 @@
  *   - return 0 on success; SCL_ERR_* (<0) on bad arguments / unsupported shapes;
  *     -1000 - cudaError_t on a CUDA runtime failure; scl_error_string() decodes all of them
  *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16
- *   - feature matrices are row-major [rows, D] with D % 64 == 0 and D <= 512
+ *   - feature matrices are row-major [rows, D]; D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 (768, 1024:
+ *     CTA-pair kernels only; the backward then runs two D slices and recomputes the similarity tile per slice)
  */
 #ifndef SCL_B200_H_
 #define SCL_B200_H_
@@ -51,7 +52,7 @@ typedef struct scl_plan {
   int n_slots;         /* fwd: partial-statistics slots per row (2 or 4 per chunk)  */
   int m_pad;           /* rows padded to the 128-row MMA tile                       */
   int n_pad;           /* columns padded to the column tile                         */
-  int d_split;         /* bwd: number of D slices (1 or 2; always 1 for the CTA-pair kernel) */
+  int d_split;         /* bwd: number of D slices (single-CTA: D > 256; CTA-pair: D > 512)  */
   int variant;         /* 0 = single-CTA kernels (cta_group::1), 1 = CTA-pair kernels (cta_group::2) */
 } scl_plan;
 /* variant: 0 / 1 as above, -1 = library default (environment SCL_VARIANT=0|1 overrides the default) */

@@ -67,7 +67,12 @@ int resolve_variant(int variant) {
   return kDefaultVariant;
 }
 
-bool shape_ok(int m_rows, int n_cols, int d) { return m_rows >= 1 && n_cols >= 1 && d >= 64 && d <= 512 && d % 64 == 0; }
+// D % 64 == 0 up to 512; 768 and 1024-class widths (D % 256 == 0 up to 1024) run on the CTA-pair kernels only
+bool shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
+  if (m_rows < 1 || n_cols < 1 || d < 64) return false;
+  if (d <= 512) return d % 64 == 0;
+  return variant == 1 && d <= 1024 && d % 256 == 0;
+}
 
 }  // namespace
 
@@ -79,7 +84,8 @@ const char* scl_error_string(int code) {
   switch (code) {
     case SCL_OK: return "ok";
     case SCL_ERR_INVALID_ARG: return "invalid argument (null / misaligned pointer or bad size)";
-    case SCL_ERR_UNSUPPORTED_SHAPE: return "unsupported shape (need D % 64 == 0, 64 <= D <= 512, rows >= 1)";
+    case SCL_ERR_UNSUPPORTED_SHAPE:
+      return "unsupported shape (need rows >= 1 and D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 on the CTA-pair kernels)";
     case SCL_ERR_NO_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the CUDA driver";
     case SCL_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled rejected the tensor map";
     case SCL_ERR_NOT_SM100: return "device is not compute capability 10.x (kernels are sm_100a only)";
@@ -106,6 +112,7 @@ int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0;
   plan->variant = resolve_variant(variant);
+  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   if (plan->variant == 1) {
     plan->chunks = scl::fwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
     plan->m_pad = (m_rows + 255) / 256 * 256;
@@ -125,12 +132,13 @@ int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0, nds = 0, dn = 0;
   plan->variant = resolve_variant(variant);
+  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   plan->m_pad = (m_rows + 127) / 128 * 128;
   plan->n_slots = 0;
   if (plan->variant == 1) {
-    plan->chunks = scl::bwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+    plan->chunks = scl::bwd_pair_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
     plan->n_pad = (n_cols + 255) / 256 * 256;
-    plan->d_split = 1;
+    plan->d_split = scl::bwd_pair_d_slices(d);
   } else {
     scl::bwd_pick_split(d, &nds, &dn);
     if (dn % 32 != 0) return SCL_ERR_UNSUPPORTED_SHAPE;
@@ -176,7 +184,7 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
                      void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr)
     return SCL_ERR_INVALID_ARG;
-  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_rows, tm_cols;
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
@@ -237,7 +245,7 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
   if (x_rows == nullptr || y_cols == nullptr || y_cols_t == nullptr || scalars3 == nullptr || plan == nullptr ||
       row_coef == nullptr || col_coef == nullptr || dx_partial == nullptr || ld_t < n_cols)
     return SCL_ERR_INVALID_ARG;
-  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int nds = 0, dn = 0;
   scl::bwd_pick_split(d, &nds, &dn);
   CUtensorMap tm_rows, tm_cols, tm_cols_t;

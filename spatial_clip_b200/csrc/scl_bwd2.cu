@@ -61,23 +61,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
 bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
                      const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
                      const __grid_constant__ CUtensorMap tm_cols_t,  // Y^T [D, N]  box {64, 128}
-                     int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad, int diag0,
-                     const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
+                     int m_rows, int n_cols, int d, int d_slices, int n_tiles, int tiles_per_chunk, int m_pad,
+                     int diag0, const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
                      const float4* __restrict__ col_coef, float* __restrict__ dx_partial,
                      long long* __restrict__ dbg_t) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ B2Bars bars;
   const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
-  long long* my_t = timed ? dbg_t + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  long long* my_t = timed ? dbg_t + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16
+                          : nullptr;
   const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kB2BK;
-  uint8_t* smem_x = smem;                                // nk x 8 KB, stationary
-  uint8_t* smem_g = smem_x + nk * kB2XChunkBytes;        // 32 KB, single buffer (see g_full / g_empty)
+  // D <= 512: one D slice, X block resident.  D > 512 (TMEM cannot hold dX[64 x D]): blockIdx.z selects a
+  // slice of ds = D / d_slices output columns; z is still contracted over all of D, with the X chunks
+  // streamed through the ring next to the Y chunks.
+  const bool stream_x = d_slices > 1;
+  const int ds = d / d_slices;
+  const int d0 = static_cast<int>(blockIdx.z) * ds;
+  uint8_t* smem_x = smem;                                // nk x 8 KB, stationary (absent when streamed)
+  uint8_t* smem_g = smem_x + (stream_x ? 0 : nk * kB2XChunkBytes);  // 32 KB, single buffer
   uint8_t* smem_ring = smem_g + kB2GBytes;               // 3 x 32 KB
   uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
-  const int ng = (d + 255) / 256;  // accumulator groups of up to 256 output columns
+  const int ng = (ds + 255) / 256;  // accumulator groups of up to 256 output columns
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -120,17 +127,19 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   if (warp == kB2ProducerWarp) {
     // ------------------------------------------------------------ TMA producer (one thread per CTA)
     if (lane == 0) {
-      if (leader) mbar_arrive_expect_tx(&bars.x_full, static_cast<uint32_t>(2 * nk * kB2XChunkBytes));
-      for (int kc = 0; kc < nk; ++kc)
-        tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
+      if (!stream_x) {
+        if (leader) mbar_arrive_expect_tx(&bars.x_full, static_cast<uint32_t>(2 * nk * kB2XChunkBytes));
+        for (int kc = 0; kc < nk; ++kc)
+          tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
+      }
       int ring_s = 0;
       uint32_t ring_ph = 0;
       long long w_empty = 0, w_ce = 0;
       // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
-      auto acquire = [&](int n_boxes) {
+      auto acquire = [&](int bytes_per_cta) {
         const int s = ring_s;
         mbar_wait_t(&bars.empty[s], ring_ph ^ 1, timed, w_empty);
-        if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * n_boxes * kB2SlotBytes));
+        if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
         if (++ring_s == kB2Stages) {
           ring_s = 0;
           ring_ph ^= 1;
@@ -145,12 +154,20 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
         const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
-        for (int kc = 0; kc < nk; kc += 2) {
-          const int nb = min(2, nk - kc);
-          const int s = acquire(nb);
-          for (int b = 0; b < nb; ++b)
-            tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
-                             (kc + b) * kB2BK, col0);
+        if (stream_x) {  // one K chunk per stage: Y chunk in slot 0, X chunk (8 KB) in slot 1
+          for (int kc = 0; kc < nk; ++kc) {
+            const int s = acquire(kB2SlotBytes + kB2XChunkBytes);
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK, row0);
+          }
+        } else {
+          for (int kc = 0; kc < nk; kc += 2) {
+            const int nb = min(2, nk - kc);
+            const int s = acquire(nb * kB2SlotBytes);
+            for (int b = 0; b < nb; ++b)
+              tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
+                               (kc + b) * kB2BK, col0);
+          }
         }
       };
       auto push_yt = [&](int lt) {
@@ -158,12 +175,12 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
         for (int u = 0; u < n_units; u += 2) {
           const int nb = min(2, n_units - u);
-          const int s = acquire(nb);
+          const int s = acquire(nb * kB2SlotBytes);
           for (int b = 0; b < nb; ++b) {
             const int js = (u + b) / ng, g = (u + b) % ng;
-            const int n_g = min(256, d - 256 * g);
+            const int n_g = min(256, ds - 256 * g);
             tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
-                             col0 + js * 64, 256 * g + static_cast<int>(cta) * (n_g / 2));
+                             col0 + js * 64, d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
           }
         }
       };
@@ -186,7 +203,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
       long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
-      mbar_wait_warp(&bars.x_full, 0, timed, w_x);
+      if (!stream_x) mbar_wait_warp(&bars.x_full, 0, timed, w_x);
       tc_fence_after();
       int ring_s = 0;
       uint32_t ring_ph = 0;
@@ -201,14 +218,16 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
-        for (int kc = 0; kc < nk; kc += 2, advance()) {
-          const int nb = min(2, nk - kc);
+        const int kstep = stream_x ? 1 : 2;
+        for (int kc = 0; kc < nk; kc += kstep, advance()) {
+          const int nb = min(kstep, nk - kc);
           const int s = ring_s;
           mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fz);
           tc_fence_after();
           if (elect_one()) {
             for (int b = 0; b < nb; ++b) {
-              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_x + (kc + b) * kB2XChunkBytes));
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(
+                  stream_x ? smem_ring + s * kB2StageBytes + kB2SlotBytes : smem_x + (kc + b) * kB2XChunkBytes));
               const uint64_t b_desc =
                   umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
 #pragma unroll
@@ -233,7 +252,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           if (elect_one()) {
             for (int b = 0; b < nb; ++b) {
               const int js = (u + b) / ng, g = (u + b) % ng;
-              const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, d - 256 * g));
+              const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g));
               const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_g + js * kB2GSubBytes));
               const uint64_t b_desc =
                   umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
@@ -353,12 +372,12 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     tc_fence_after();
     float* out_row = dx_partial + (static_cast<size_t>(blockIdx.y) * m_pad + row0 + r_loc) * d;
     for (int g = 0; g < ng; ++g) {
-      const int n_g = min(256, d - 256 * g);
+      const int n_g = min(256, ds - 256 * g);
       if (hh * 32 < n_g / 2) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + hh * 32, r);
         tmem_ld_wait();
-        float* dst = out_row + 256 * g + n_half * (n_g / 2) + hh * 32;
+        float* dst = out_row + d0 + 256 * g + n_half * (n_g / 2) + hh * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -374,9 +393,11 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   }
 }
 
+int bwd_pair_d_slices(int d) { return d > 512 ? 2 : 1; }
+
 size_t bwd_pair_smem_bytes(int d) {
-  return 1024 + static_cast<size_t>(d / kB2BK) * kB2XChunkBytes + kB2GBytes + kB2Stages * kB2StageBytes +
-         2 * kB2CoefBytes;
+  const size_t x_block = d > 512 ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
+  return 1024 + x_block + kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
 }
 
 // Column chunking for a grid of `units` row blocks (CTAs or CTA pairs) over `slots` concurrently resident
@@ -401,8 +422,8 @@ static int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles
   *tiles_per_chunk = best_tpc;
   return best_c;
 }
-int bwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {
-  const int pairs = (m_rows + 127) / 128;
+int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
+  const int pairs = (m_rows + 127) / 128 * (d > 512 ? 2 : 1);
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
@@ -417,8 +438,9 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
   if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 127) / 128;
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
-  dim3 grid(2 * pairs, chunks);
-  bwd_rows_pair_kernel<<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, n_tiles,
+  const int d_slices = bwd_pair_d_slices(d);
+  dim3 grid(2 * pairs, chunks, d_slices);
+  bwd_rows_pair_kernel<<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices, n_tiles,
                                                            tiles_per_chunk, m_pad, diag0, scale_log2, row_coef,
                                                            col_coef, dx_partial, dbg_t);
   return cudaGetLastError();

@@ -57,8 +57,12 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
   const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kF2BK;
+  // D <= 512: the X block stays resident (nk x 16 KB) and the ring carries only Y chunks (16 KB stages).
+  // D  > 512: X no longer fits next to a useful ring, so X chunks stream with the Y chunks (32 KB stages).
+  const bool stream_x = d > 512;
+  const int stage_bytes = stream_x ? 2 * kF2BStageBytes : kF2BStageBytes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + nk * kF2AChunkBytes;
+  uint8_t* smem_b = smem + (stream_x ? 0 : nk * kF2AChunkBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,9 +99,11 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
   if (warp == kF2ProducerWarp) {
     // ------------------------------------------------------------ TMA producer (one thread per CTA)
     if (lane == 0) {
-      if (leader) mbar_arrive_expect_tx(&bars.a_full, static_cast<uint32_t>(2 * nk * kF2AChunkBytes));
-      for (int kc = 0; kc < nk; ++kc)
-        tma_load_2d_pair(smem_a + kc * kF2AChunkBytes, &tm_rows, &bars.a_full, kc * kF2BK, row0);
+      if (!stream_x) {
+        if (leader) mbar_arrive_expect_tx(&bars.a_full, static_cast<uint32_t>(2 * nk * kF2AChunkBytes));
+        for (int kc = 0; kc < nk; ++kc)
+          tma_load_2d_pair(smem_a + kc * kF2AChunkBytes, &tm_rows, &bars.a_full, kc * kF2BK, row0);
+      }
       int it = 0;
       long long w_empty = 0;
       for (int lt = 0; lt < n_my; ++lt) {
@@ -105,8 +111,10 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
           mbar_wait_t(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1, timed, w_empty);
-          if (leader) mbar_arrive_expect_tx(&bars.full[s], 2 * kF2BStageBytes);
-          tma_load_2d_pair(smem_b + s * kF2BStageBytes, &tm_cols, &bars.full[s], kc * kF2BK, col0);
+          if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * stage_bytes));
+          tma_load_2d_pair(smem_b + s * stage_bytes, &tm_cols, &bars.full[s], kc * kF2BK, col0);
+          if (stream_x)
+            tma_load_2d_pair(smem_b + s * stage_bytes + kF2BStageBytes, &tm_rows, &bars.full[s], kc * kF2BK, row0);
         }
       }
       if (timed) {
@@ -121,7 +129,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
       long long w_a = 0, w_te = 0, w_full = 0;
-      mbar_wait_warp(&bars.a_full, 0, timed, w_a);
+      if (!stream_x) mbar_wait_warp(&bars.a_full, 0, timed, w_a);
       tc_fence_after();
       int it = 0;
       for (int lt = 0; lt < n_my; ++lt) {
@@ -134,8 +142,9 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
           mbar_wait_warp(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + kc * kF2AChunkBytes));
-            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + s * kF2BStageBytes));
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(
+                stream_x ? smem_b + s * stage_bytes + kF2BStageBytes : smem_a + kc * kF2AChunkBytes));
+            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + s * stage_bytes));
 #pragma unroll
             for (int k = 0; k < kF2BK / 16; ++k)  // +32 B per K step == +2 in the descriptor's 16-byte address field
               tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
@@ -267,6 +276,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
 }
 
 size_t fwd_pair_smem_bytes(int d) {
+  if (d > 512) return 1024 + static_cast<size_t>(kF2Stages) * 2 * kF2BStageBytes;  // streamed X: 6 x 32 KB
   return 1024 + static_cast<size_t>(d / kF2BK) * kF2AChunkBytes + kF2Stages * kF2BStageBytes;
 }
 

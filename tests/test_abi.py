@@ -43,7 +43,10 @@ def test_plans_and_errors_without_gpu(lib):
     assert lib.scl_bwd_plan(300, 300, 512, 0, ctypes.byref(p)) == 0
     assert p.m_pad == 384 and p.n_pad == 384 and p.d_split == 2
     assert lib.scl_fwd_plan(128, 128, 96, -1, ctypes.byref(p)) == -2  # D % 64 != 0
-    assert lib.scl_fwd_plan(128, 128, 1024, -1, ctypes.byref(p)) == -2  # D > 512 (this round)
+    assert lib.scl_fwd_plan(128, 128, 1024, 0, ctypes.byref(p)) == -2  # D > 512 needs the CTA-pair kernels
+    assert lib.scl_fwd_plan(128, 128, 1024, 1, ctypes.byref(p)) == 0
+    assert lib.scl_bwd_plan(128, 128, 768, 1, ctypes.byref(p)) == 0 and p.d_split == 2
+    assert lib.scl_fwd_plan(128, 128, 640, 1, ctypes.byref(p)) == -2  # D > 512 must be a multiple of 256
     assert b"unsupported shape" in lib.scl_error_string(-2)
     assert lib.scl_bwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
     assert p.variant == 1 and p.m_pad == 384 and p.n_pad == 512 and p.d_split == 1

@@ -382,3 +382,75 @@ def test_multi_rank_on_one_gpu(ops, name):
         assert abs(loss - gold["loss"][rank]) <= 1e-3 * abs(gold["loss"][rank]) + 2e-6 * meta["scale"], rep
         assert abs(ds - gold["d_scale"][rank]) <= 3e-2 * abs(gold["d_scale"][rank]) + 1e-5, rep
         assert rep[6] <= 3e-2 and rep[7] <= 3e-2, rep
+
+
+# ---------------------------------------------------------------- wide embeddings (ViT-L / ViT-H: D = 768, 1024)
+@pytest.mark.parametrize("m,n,d", [(300, 700, 768), (257, 1025, 1024)])
+def test_wide_embeddings_kernels(ops, m, n, d):
+    """D > 512: streamed-X forward, two-slice backward (CTA-pair kernels only)."""
+    from dense_checker import row_stats
+    from emulated_ops import EmulatedOps
+
+    if ops.variant == 0:
+        from spatial_clip_b200._cuda import SclError
+
+        x, y = _bf16_pair(64, 64, d, seed=1)
+        with pytest.raises(SclError):
+            ops.fwd_rowstats(x, y, ops.prep_scalars(torch.tensor([20.0], device="cuda"), None))
+        return
+    x, y = _bf16_pair(m, n, d, seed=m + n + d)
+    s = 30.0
+    scal = ops.prep_scalars(torch.tensor([s], device="cuda"), None)
+    part, plan, z = ops.fwd_rowstats(x, y, scal, debug_z=True)
+    assert (z - x.float() @ y.float().t()).abs().max().item() < 3e-5
+    col = torch.full((m, 1), -1, dtype=torch.int32, device="cuda")
+    q = torch.zeros((m, 1), device="cuda")
+    stats = ops.row_finalize(part, plan, x, y, col, q).double()
+    _, lse, mu, var = row_stats(x, y, s)
+    assert (stats[:, 0] * LN2 - lse).abs().max().item() < 2e-5 * s
+    assert (stats[:, 1] - mu).abs().max().item() < 2e-5
+    # backward pass alone
+    zz = x.float() @ y.float().t()
+    rs = torch.stack([torch.logsumexp(s * zz, 1) * LOG2E, 0.1 * torch.rand(m).cuda(), torch.zeros(m).cuda(),
+                      torch.zeros(m).cuda()], 1).contiguous()
+    cs = torch.stack([torch.logsumexp(s * zz, 0) * LOG2E, 0.1 * torch.rand(n).cuda(), torch.zeros(n).cuda(),
+                      torch.zeros(n).cuda()], 1).contiguous()
+    ocol = torch.full((n, 1), -1, dtype=torch.int32, device="cuda")
+    oq = torch.zeros((n, 1), device="cuda")
+    gaps = torch.tensor([0.2], device="cuda")
+    go = torch.tensor([1.3], device="cuda")
+    ld_t = (n + 7) // 8 * 8
+    _, y_t = ops.cast_bf16(y, want_rows=False, want_t=True, ld_t=ld_t)
+    args = (rs, cs, col, q, ocol, oq, max(m, n), 0, gaps, scal, go, 0.5 / m, 0.05, 1.0, 2, torch.float32)
+    got = ops.bwd_rows(x, y, y_t, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
+    torch.cuda.synchronize()
+    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), y_t.cpu(), *[a.cpu() if torch.is_tensor(a) else a for a in args])
+    assert (got.cpu() - want).abs().max().item() <= 1.2e-2 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("d", [768, 1024])
+def test_wide_embeddings_module_vs_oracle(ops, d):
+    if ops.variant == 0:
+        pytest.skip("single-CTA kernels stop at D = 512")
+    from spatial_clip_b200 import SpatialLoss
+
+    gen = dict(n=300, d=d, k=8, seed=4000 + d, dup_frac=0.01, self_loops=True)
+    b = make_spot_batch(**gen)
+    cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+               neighbor_alpha_scale=0.5, float32_logits=True)
+    img = b.image_features.cuda().requires_grad_(True)
+    txt = b.text_features.cuda().requires_grad_(True)
+    s = torch.tensor(55.0, device="cuda", requires_grad=True)
+    ids = b.tile_ids.cuda()
+    loss = SpatialLoss(**cfg)(img, txt, s, ids, ids, b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())[
+        "contrastive_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    orc = spatial_loss_oracle(b.image_features.bfloat16().float().numpy(), b.text_features.bfloat16().float().numpy(),
+                              55.0, b.tile_ids.numpy(), b.tile_ids.numpy(), b.neighbor_tile_ids.numpy(),
+                              b.neighbor_alphas.numpy(), 1, 40.0, 0.05, 0.5)
+    r0 = orc.ranks[0]
+    assert abs(float(loss.detach()) - r0.loss) <= 2e-5 * abs(r0.loss) + 1e-4
+    assert abs(float(s.grad) - r0.d_scale) <= 1e-3 * abs(r0.d_scale) + 2e-6
+    for got, ref in ((img.grad.cpu().numpy(), orc.d_image), (txt.grad.cpu().numpy(), orc.d_text)):
+        assert np.abs(got - ref).max() <= 1.2e-2 * np.abs(ref).max()
