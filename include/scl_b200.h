@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SCL_ABI_VERSION 2
+#define SCL_ABI_VERSION 3
 #define SCL_OK 0
 #define SCL_ERR_INVALID_ARG (-1)
 #define SCL_ERR_UNSUPPORTED_SHAPE (-2)
@@ -121,6 +121,51 @@ int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, in
                    const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                    const float* scalars3, const float* grad_out, float c, float w, float mult, int col_mode,
                    float* dx32, void* dx_out, int out_dtype, void* stream);
+
+/* ---- composite entry points: one host call per phase ----------------------------------------------
+ * The per-step host cost (ctypes calls, work-area allocations) matters once the batch is sharded over 8 GPUs and a
+ * rank's kernels take ~1 ms; these chain the launches above on the given stream.  All pointers as above. */
+typedef struct scl_prepare_args {
+  const void* image; const void* text; int src_dtype;     /* [rows, d] inputs of the loss modules          */
+  const float* logit_scale; float cap;                     /* cap <= 0: none                                */
+  int rows, d, ld_t;
+  void* image_bf16; void* text_bf16;                       /* [rows, d] bf16 (required)                     */
+  void* image_bf16_t; void* text_bf16_t;                   /* [d, ld_t] bf16 transposed copies or NULL      */
+  float* scalars3;
+} scl_prepare_args;
+int scl_prepare(const scl_prepare_args* a, void* stream);
+
+typedef struct scl_fwd_args {
+  const void* img_l; const void* txt_l;                    /* local rows  [b_local, d] bf16                 */
+  const void* img_all; const void* txt_all;                /* gathered    [n_global, d] bf16                */
+  int b_local, n_global, d, rank, variant;
+  const float* scalars3;
+  const int64_t* img_ids_all; const int64_t* txt_ids_all;  /* gathered tile ids (k > 0)                     */
+  const int64_t* nbr_ids; const float* nbr_alpha;          /* [b_local, k]                                  */
+  int k; float alpha_scale; int same_ids;
+  float c, w; int finalize_scalars;                        /* 0: stop after sums6 (caller exchanges them)   */
+  int32_t* col_it; float* w_it; float* q_it;               /* image rows -> text columns  [b_local, k+1]    */
+  int32_t* col_ti; float* w_ti; float* q_ti;               /* text rows -> image columns (may alias *_it)   */
+  void* stats_i; void* stats_t;                            /* float4[b_local]                               */
+  float* sums6; float* out4;
+  void* workspace; size_t workspace_bytes;                 /* >= scl_fwd_workspace_bytes(...)               */
+} scl_fwd_args;
+size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant);
+int scl_fwd_all(const scl_fwd_args* a, void* stream);
+
+typedef struct scl_bwd_args {
+  const void* x_rows; const void* y_all; const void* y_all_t; int ld_t;
+  int b_local, n_global, d, rank, variant;
+  const void* row_stats; const void* col_stats_all;        /* float4[b_local], float4[n_global]             */
+  const int32_t* pos_col; const float* pos_q; const float* opp_q_local;
+  const int32_t* opp_col_all; const float* opp_q_all; int k_plus_1;
+  const float* gaps; const float* scalars3; const float* grad_out;
+  float c, w, mult; int col_mode;
+  void* dx_out; int out_dtype;                             /* [b_local, d]                                  */
+  void* workspace; size_t workspace_bytes;                 /* >= scl_bwd_workspace_bytes(...)               */
+} scl_bwd_args;
+size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int variant);
+int scl_bwd_dir(const scl_bwd_args* a, void* stream);
 
 /* ---- statistics exchange helper (replaces torch.distributed.nn's reduce-scatter in backward) ----
  * gathered: float[world][rec_floats], the all-gathered flat per-rank records (host arrays outs/offs/lens of

@@ -25,6 +25,32 @@ class SclError(RuntimeError):
     pass
 
 
+_VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class PrepareArgs(C.Structure):
+    _fields_ = [("image", _VP), ("text", _VP), ("src_dtype", _I), ("logit_scale", _VP), ("cap", _F), ("rows", _I),
+                ("d", _I), ("ld_t", _I), ("image_bf16", _VP), ("text_bf16", _VP), ("image_bf16_t", _VP),
+                ("text_bf16_t", _VP), ("scalars3", _VP)]
+
+
+class FwdArgs(C.Structure):
+    _fields_ = [("img_l", _VP), ("txt_l", _VP), ("img_all", _VP), ("txt_all", _VP), ("b_local", _I), ("n_global", _I),
+                ("d", _I), ("rank", _I), ("variant", _I), ("scalars3", _VP), ("img_ids_all", _VP),
+                ("txt_ids_all", _VP), ("nbr_ids", _VP), ("nbr_alpha", _VP), ("k", _I), ("alpha_scale", _F),
+                ("same_ids", _I), ("c", _F), ("w", _F), ("finalize_scalars", _I), ("col_it", _VP), ("w_it", _VP),
+                ("q_it", _VP), ("col_ti", _VP), ("w_ti", _VP), ("q_ti", _VP), ("stats_i", _VP), ("stats_t", _VP),
+                ("sums6", _VP), ("out4", _VP), ("workspace", _VP), ("workspace_bytes", _SZ)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [("x_rows", _VP), ("y_all", _VP), ("y_all_t", _VP), ("ld_t", _I), ("b_local", _I), ("n_global", _I),
+                ("d", _I), ("rank", _I), ("variant", _I), ("row_stats", _VP), ("col_stats_all", _VP), ("pos_col", _VP),
+                ("pos_q", _VP), ("opp_q_local", _VP), ("opp_col_all", _VP), ("opp_q_all", _VP), ("k_plus_1", _I),
+                ("gaps", _VP), ("scalars3", _VP), ("grad_out", _VP), ("c", _F), ("w", _F), ("mult", _F),
+                ("col_mode", _I), ("dx_out", _VP), ("out_dtype", _I), ("workspace", _VP), ("workspace_bytes", _SZ)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "scl_abi_version": (C.c_int, []),
@@ -55,6 +81,11 @@ EXPORTS = {
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
+    "scl_prepare": (C.c_int, [C.POINTER(PrepareArgs), C.c_void_p]),
+    "scl_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "scl_fwd_all": (C.c_int, [C.POINTER(FwdArgs), C.c_void_p]),
+    "scl_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "scl_bwd_dir": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
     "scl_unpack_records": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.c_void_p]),
 }
@@ -76,7 +107,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 2:
+    if lib.scl_abi_version() != 3:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -259,6 +290,85 @@ class CudaOps:
             self._check(self.lib.scl_loss_scalars(_ptr(sums6), _ptr(scalars), float(c), float(w), _ptr(out), st),
                         "scl_loss_scalars")
         self.launches += 1
+        return out
+
+    # ---------------------------------------------------------------- composite phases (one host call each)
+    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t):
+        """cap + bf16 casts (+ transposed copies) of both modalities: scl_prepare."""
+        st = self._stream(image)
+        rows, d = image.shape
+        if text.dtype != image.dtype:
+            text = text.to(image.dtype)
+        img = self.empty((rows, d), torch.bfloat16, image)
+        txt = self.empty((rows, d), torch.bfloat16, image)
+        new_t = torch.zeros if ld_t != rows else torch.empty
+        img_t = new_t((d, ld_t), dtype=torch.bfloat16, device=image.device) if want_img_t else None
+        txt_t = new_t((d, ld_t), dtype=torch.bfloat16, device=image.device) if want_txt_t else None
+        scal = self.empty((3,), torch.float32, image)
+        a = PrepareArgs(_ptr(image), _ptr(text), _DTYPE_CODE[image.dtype], _ptr(logit_scale),
+                        float(cap) if cap is not None else -1.0, rows, d, ld_t, _ptr(img), _ptr(txt), _ptr(img_t),
+                        _ptr(txt_t), _ptr(scal))
+        with _DeviceGuard(image.device):
+            self._check(self.lib.scl_prepare(C.byref(a), st), "scl_prepare")
+        self.launches += 3
+        return img, txt, img_t, txt_t, scal
+
+    def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
+                    finalize_scalars):
+        """Soft targets + both fused similarity/LSE passes + reductions: scl_fwd_all.
+        ids = None (plain CLIP) or (img_ids_all, txt_ids_all, nbr_ids, nbr_alpha, same_ids)."""
+        st = self._stream(img_l)
+        n, d = img_all.shape
+        kp1 = k + 1
+        dev = img_l.device
+        same = ids is None or ids[4]
+        lists = torch.empty((2 if not same else 1, 3, b_local, kp1), dtype=torch.float32, device=dev)
+        col_it, w_it, q_it = lists[0, 0].view(torch.int32), lists[0, 1], lists[0, 2]
+        if same:
+            col_ti, w_ti, q_ti = col_it, w_it, q_it
+        else:
+            col_ti, w_ti, q_ti = lists[1, 0].view(torch.int32), lists[1, 1], lists[1, 2]
+        small = torch.empty((2 * b_local + 3, 4), dtype=torch.float32, device=dev)
+        stats_i, stats_t = small[:b_local], small[b_local:2 * b_local]
+        sums6 = small[2 * b_local:2 * b_local + 2].reshape(-1)[:6]
+        out4 = small[2 * b_local + 2]
+        ws_bytes = self.lib.scl_fwd_workspace_bytes(b_local, n, d, k, self.variant)
+        if ws_bytes == 0:
+            self._check(-2, "scl_fwd_workspace_bytes")
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        a = FwdArgs(_ptr(img_l), _ptr(txt_l), _ptr(img_all), _ptr(txt_all), b_local, n, d, rank, self.variant,
+                    _ptr(scalars), _ptr(ids[0]) if ids else None, _ptr(ids[1]) if ids else None,
+                    _ptr(ids[2]) if ids else None, _ptr(ids[3]) if ids else None, k, float(alpha_scale), int(same),
+                    float(c), float(w), int(finalize_scalars), _ptr(col_it), _ptr(w_it), _ptr(q_it), _ptr(col_ti),
+                    _ptr(w_ti), _ptr(q_ti), _ptr(stats_i), _ptr(stats_t), _ptr(sums6), _ptr(out4), _ptr(ws), ws_bytes)
+        with _DeviceGuard(dev):
+            self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
+        self.launches += (3 if k > 0 else 1) * (1 if same else 2) + 5 + (1 if finalize_scalars else 0)
+        return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4
+
+    def backward_dir(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+                     b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local):
+        """dX of the local rows for one direction: scl_bwd_dir (coefficients + fused tensor-core pass + sparse finish).
+        With kernel timing on (bench.py roofline) the three launches are issued separately."""
+        if self.kernel_events is not None or getattr(self, "cycle_buffers", None) is not None:
+            return self.bwd_rows(x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+                                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype,
+                                 opp_q_local=opp_q_local)
+        st = self._stream(x_rows)
+        m, d = x_rows.shape
+        n = y_all.shape[0]
+        ws_bytes = self.lib.scl_bwd_workspace_bytes(m, n, d, self.variant)
+        if ws_bytes == 0:
+            self._check(-2, "scl_bwd_workspace_bytes")
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x_rows.device)
+        out = self.empty((m, d), out_dtype, x_rows)
+        a = BwdArgs(_ptr(x_rows), _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], m, n, d, rank, self.variant,
+                    _ptr(row_stats), _ptr(col_stats), _ptr(pos_col), _ptr(pos_q), _ptr(opp_q_local),
+                    _ptr(opp_col_all), _ptr(opp_q_all), pos_col.shape[1], _ptr(gaps), _ptr(scalars), _ptr(grad_out),
+                    float(c), float(w), float(mult), col_mode, _ptr(out), _DTYPE_CODE[out_dtype], _ptr(ws), ws_bytes)
+        with _DeviceGuard(x_rows.device):
+            self._check(self.lib.scl_bwd_dir(C.byref(a), st), "scl_bwd_dir")
+        self.launches += 3 + (1 if col_mode != 0 else 0) + (1 if out_dtype != torch.float32 else 0)
         return out
 
     def exchange_records(self, parts, world, gather_fn):

@@ -290,6 +290,103 @@ int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, in
                                         static_cast<cudaStream_t>(stream)));
 }
 
+namespace {
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+}  // namespace
+
+int scl_prepare(const scl_prepare_args* a, void* stream) {
+  if (a == nullptr || a->image == nullptr || a->text == nullptr || a->image_bf16 == nullptr ||
+      a->text_bf16 == nullptr || a->scalars3 == nullptr || a->logit_scale == nullptr)
+    return SCL_ERR_INVALID_ARG;
+  int rc = scl_prep_scalars(a->logit_scale, a->cap, a->scalars3, stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_cast_bf16(a->image, a->src_dtype, a->image_bf16, a->image_bf16_t, a->rows, a->d, a->ld_t, 0, stream);
+  if (rc != SCL_OK) return rc;
+  return scl_cast_bf16(a->text, a->src_dtype, a->text_bf16, a->text_bf16_t, a->rows, a->d, a->ld_t, 0, stream);
+}
+
+size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant) {
+  scl_plan p;
+  if (scl_fwd_plan(b_local, n_global, d, variant, &p) != SCL_OK) return 0;
+  const size_t partial = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
+  const size_t hash = k > 0 ? align256(scl::positives_hash_bytes(n_global)) : 0;
+  return 2 * partial + hash;
+}
+
+int scl_fwd_all(const scl_fwd_args* a, void* stream) {
+  if (a == nullptr || a->workspace == nullptr) return SCL_ERR_INVALID_ARG;
+  scl_plan p;
+  int rc = scl_fwd_plan(a->b_local, a->n_global, a->d, a->variant, &p);
+  if (rc != SCL_OK) return rc;
+  if (a->workspace_bytes < scl_fwd_workspace_bytes(a->b_local, a->n_global, a->d, a->k, a->variant))
+    return SCL_ERR_INVALID_ARG;
+  const size_t partial_bytes = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
+  char* ws = static_cast<char*>(a->workspace);
+  void* part_i = ws;
+  void* part_t = ws + partial_bytes;
+  void* hash = ws + 2 * partial_bytes;
+  const size_t hash_bytes = a->k > 0 ? scl::positives_hash_bytes(a->n_global) : 0;
+  // soft targets: image rows use the text-id map, text rows the image-id map (losses.py:102-108)
+  rc = scl_build_positives(a->txt_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
+                           a->rank, a->k > 0 ? hash : nullptr, hash_bytes, a->col_it, a->w_it, a->q_it, stream);
+  if (rc != SCL_OK) return rc;
+  if (!a->same_ids && a->k > 0) {
+    rc = scl_build_positives(a->img_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
+                             a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti, stream);
+    if (rc != SCL_OK) return rc;
+  }
+  rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
+                        nullptr, stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1, a->stats_i,
+                        stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_fwd_rowstats(a->txt_l, a->b_local, a->img_all, a->n_global, a->d, a->scalars3, &p, part_t, nullptr, 0,
+                        nullptr, stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_row_finalize(part_t, &p, a->b_local, a->d, a->txt_l, a->img_all, a->col_ti, a->q_ti, a->k + 1, a->stats_t,
+                        stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_reduce_rows(a->stats_i, a->stats_t, a->b_local, a->scalars3, a->sums6, stream);
+  if (rc != SCL_OK) return rc;
+  if (a->finalize_scalars) rc = scl_loss_scalars(a->sums6, a->scalars3, a->c, a->w, a->out4, stream);
+  return rc;
+}
+
+size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int variant) {
+  scl_plan p;
+  if (scl_bwd_plan(b_local, n_global, d, variant, &p) != SCL_OK) return 0;
+  return align256(static_cast<size_t>(p.m_pad) * 16) + align256(static_cast<size_t>(p.n_pad) * 16) +
+         align256(static_cast<size_t>(p.chunks) * p.m_pad * d * 4) + align256(static_cast<size_t>(b_local) * d * 4);
+}
+
+int scl_bwd_dir(const scl_bwd_args* a, void* stream) {
+  if (a == nullptr || a->workspace == nullptr || a->dx_out == nullptr) return SCL_ERR_INVALID_ARG;
+  scl_plan p;
+  int rc = scl_bwd_plan(a->b_local, a->n_global, a->d, a->variant, &p);
+  if (rc != SCL_OK) return rc;
+  if (a->workspace_bytes < scl_bwd_workspace_bytes(a->b_local, a->n_global, a->d, a->variant))
+    return SCL_ERR_INVALID_ARG;
+  char* ws = static_cast<char*>(a->workspace);
+  void* row_coef = ws;
+  ws += align256(static_cast<size_t>(p.m_pad) * 16);
+  void* col_coef = ws;
+  ws += align256(static_cast<size_t>(p.n_pad) * 16);
+  float* partial = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(p.chunks) * p.m_pad * a->d * 4);
+  float* dx32 = a->out_dtype == 0 ? static_cast<float*>(a->dx_out) : reinterpret_cast<float*>(ws);
+  rc = scl_bwd_coeffs(a->row_stats, a->b_local, a->col_stats_all, a->n_global, &p, a->b_local, a->rank, a->gaps,
+                      a->scalars3, a->grad_out, a->c, a->w, a->mult, a->col_mode, a->pos_q, a->opp_q_local,
+                      a->k_plus_1, row_coef, col_coef, stream);
+  if (rc != SCL_OK) return rc;
+  rc = scl_bwd_rows(a->x_rows, a->b_local, a->y_all, a->y_all_t, a->ld_t, a->n_global, a->d, a->rank * a->b_local,
+                    a->scalars3, &p, row_coef, col_coef, partial, nullptr, stream);
+  if (rc != SCL_OK) return rc;
+  return scl_bwd_finish(partial, &p, a->b_local, a->d, a->y_all, a->pos_col, a->pos_q, a->k_plus_1, a->opp_col_all,
+                        a->opp_q_all, a->n_global, a->b_local, a->rank, a->gaps, a->scalars3, a->grad_out, a->c, a->w,
+                        a->mult, a->col_mode, dx32, a->dx_out, a->out_dtype, stream);
+}
+
 int scl_unpack_records(const float* gathered, int world, int rec_floats, int n_comp, float* const* outs,
                        const int* offs, const int* lens, void* stream) {
   if (gathered == nullptr || outs == nullptr || offs == nullptr || lens == nullptr || world < 1 || rec_floats < 1)

@@ -118,61 +118,48 @@ class _ContrastiveLossFn(torch.autograd.Function):
         dev = image_features.device
 
         scale = logit_scale.detach().reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous()
-        scalars = ops.prep_scalars(scale, cfg.cap)
 
-        # ---- features: bf16 copies, gathered rank-major (gather_features, loss.py:21-65)
-        # single rank + backward wanted: the transposed copies the backward GEMMs need come out of the same
-        # pass over the fp32 inputs (dImage needs text^T, dGene needs image^T)
+        # ---- cap, bf16 copies (gather_features operands, loss.py:21-65).  Single rank + backward wanted: the
+        # transposed copies the backward GEMMs need come out of the same pass (dImage needs text^T and vice versa)
         ld_t = (n + 7) // 8 * 8
         fuse_t = world == 1  # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
-        img_l, img_t = ops.cast_bf16(image_features.detach().contiguous(),
-                                     want_t=fuse_t and ctx.needs_input_grad[1], ld_t=ld_t)
-        txt_l, txt_t = ops.cast_bf16(text_features.detach().contiguous(),
-                                     want_t=fuse_t and ctx.needs_input_grad[0], ld_t=ld_t)
+        img_l, txt_l, img_t, txt_t, scalars = ops.prepare(
+            image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap,
+            fuse_t and ctx.needs_input_grad[1], fuse_t and ctx.needs_input_grad[0], ld_t)
         if world > 1:
             img_all = _all_gather_rows(img_l, world, cfg.group)
             txt_all = _all_gather_rows(txt_l, world, cfg.group)
         else:
             img_all, txt_all = img_l, txt_l
 
-        # ---- soft targets as ELL lists (losses.py:91-111); plain CLIP = the diagonal only
+        # ---- tile ids (losses.py:63-68); plain CLIP has only the diagonal
+        ids = None
+        k = 0
         if cfg.kind == "spatial":
             k = neighbor_tile_ids.shape[1]
             same_ids = (image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
                         and image_tile_ids.shape == text_tile_ids.shape)
             img_ids = image_tile_ids.to(torch.int64).contiguous()
             txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
-            if world > 1:  # losses.py:63-68
+            if world > 1:
                 img_ids_all = _all_gather_rows(img_ids, world, cfg.group)
                 txt_ids_all = img_ids_all if same_ids else _all_gather_rows(txt_ids, world, cfg.group)
             else:
                 img_ids_all, txt_ids_all = img_ids, txt_ids
-            nbr = neighbor_tile_ids.to(torch.int64).contiguous()
-            alpha = neighbor_alphas.to(torch.float32).contiguous()
-            # image rows -> text columns use the text-id map; text rows -> image columns the image-id map
-            col_it, w_it, q_it = ops.build_positives(txt_ids_all, nbr, alpha, b_local, k, cfg.alpha_scale, rank, img_l)
-            if same_ids:
-                col_ti, w_ti, q_ti = col_it, w_it, q_it
-            else:
-                col_ti, w_ti, q_ti = ops.build_positives(img_ids_all, nbr, alpha, b_local, k, cfg.alpha_scale, rank,
-                                                         img_l)
-        else:
-            col_it, w_it, q_it = ops.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
-            col_ti, w_ti, q_ti = col_it, w_it, q_it
+            ids = (img_ids_all, txt_ids_all, neighbor_tile_ids.to(torch.int64).contiguous(),
+                   neighbor_alphas.to(torch.float32).contiguous(), same_ids)
 
-        # ---- fused similarity + online LSE, one pass per direction (losses.py:78-89, 113-121)
-        part_i, plan_i = ops.fwd_rowstats(img_l, txt_all, scalars)
-        stats_i = ops.row_finalize(part_i, plan_i, img_l, txt_all, col_it, q_it)
-        part_t, plan_t = ops.fwd_rowstats(txt_l, img_all, scalars)
-        stats_t = ops.row_finalize(part_t, plan_t, txt_l, img_all, col_ti, q_ti)
-
-        sums6 = ops.reduce_rows(stats_i, stats_t, scalars)
+        # ---- soft targets (losses.py:91-111), both fused similarity + online-LSE passes (losses.py:78-89,
+        # 113-121), row reductions and the loss scalars: one host call
         global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
+        c = 0.5 / (n if global_clip else b_local)
+        (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4 = ops.forward_all(
+            img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
+            finalize_scalars=not global_clip)
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
             # all-gather + fixed-order sum (bitwise identical on every rank, unlike an all-reduce tree)
             sums6 = _all_gather_rows(sums6.reshape(1, 6), world, cfg.group).sum(dim=0)
-        c = 0.5 / (n if global_clip else b_local)
-        out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
+            out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
 
         ctx.cfg = cfg
         ctx.c = c
@@ -217,15 +204,15 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if need_i:
             if txt_all_t is None:
                 _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
-            d_img = ops.bwd_rows(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
-                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0],
-                                 opp_q_local=q_ti)
+            d_img = ops.backward_dir(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all,
+                                     q_ti_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
+                                     ctx.in_dtypes[0], q_ti)
         if need_t:
             if img_all_t is None:
                 _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
-            d_txt = ops.bwd_rows(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
-                                 b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1],
-                                 opp_q_local=q_it)
+            d_txt = ops.backward_dir(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all,
+                                     q_it_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
+                                     ctx.in_dtypes[1], q_it)
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)

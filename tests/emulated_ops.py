@@ -100,6 +100,31 @@ class EmulatedOps:
         ds = gsum + 2 * w * gap * c * (s[4] + s[5])
         return torch.stack([loss, gap, ds, 2 * w * gap]).float()
 
+    # ---- composite phases, assembled from the per-op contracts above
+    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t):
+        img, img_t = self.cast_bf16(image, want_t=want_img_t, ld_t=ld_t)
+        txt, txt_t = self.cast_bf16(text, want_t=want_txt_t, ld_t=ld_t)
+        return img, txt, img_t, txt_t, self.prep_scalars(logit_scale, cap)
+
+    def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
+                    finalize_scalars):
+        if ids is None:
+            it = ti = self.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
+        else:
+            img_ids_all, txt_ids_all, nbr, alpha, same = ids
+            it = self.build_positives(txt_ids_all, nbr, alpha, b_local, k, alpha_scale, rank, img_l)
+            ti = it if same else self.build_positives(img_ids_all, nbr, alpha, b_local, k, alpha_scale, rank, img_l)
+        part_i, plan_i = self.fwd_rowstats(img_l, txt_all, scalars)
+        stats_i = self.row_finalize(part_i, plan_i, img_l, txt_all, it[0], it[2])
+        part_t, plan_t = self.fwd_rowstats(txt_l, img_all, scalars)
+        stats_t = self.row_finalize(part_t, plan_t, txt_l, img_all, ti[0], ti[2])
+        sums6 = self.reduce_rows(stats_i, stats_t, scalars)
+        out4 = self.loss_scalars(sums6, scalars, c, w) if finalize_scalars else None
+        return it, ti, stats_i, stats_t, sums6, out4
+
+    def backward_dir(self, *args):
+        return self.bwd_rows(*args[:-1], opp_q_local=args[-1])
+
     def exchange_records(self, parts, world, gather_fn):
         self.calls.append("exchange_records")
         flat = torch.cat([p.reshape(-1).view(torch.float32) for p in parts])
