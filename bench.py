@@ -208,8 +208,6 @@ def run_ours(args):
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush, outside the per-step event pair
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
         a.record()
         loss, _, _ = step({k: v.detach() for k, v in dev_in.items()})
         b.record()

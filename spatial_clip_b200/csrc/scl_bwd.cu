@@ -283,9 +283,15 @@ cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_co
   int n_dsplit, dn;
   bwd_pick_split(d, &n_dsplit, &dn);
   const size_t smem = bwd_smem_bytes();
-  cudaError_t err =
-      cudaFuncSetAttribute(bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int row_blocks = (m_rows + kBwdBM - 1) / kBwdBM;
   const int n_tiles = (n_cols + kBwdBN - 1) / kBwdBN;
   dim3 grid(row_blocks, n_dsplit, chunks);

@@ -433,9 +433,15 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
                                  float* dx_partial, long long* dbg_t, cudaStream_t stream) {
   const size_t smem = bwd_pair_smem_bytes(d);
-  cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int pairs = (m_rows + 127) / 128;
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);

@@ -210,9 +210,15 @@ cudaError_t launch_fwd_rowstats(const CUtensorMap& tm_rows, const CUtensorMap& t
                                 int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2, float4* partial,
                                 float* dbg_z, int dbg_ld, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes(d);
-  cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int row_blocks = (m_rows + kFwdBM - 1) / kFwdBM;
   const int n_tiles = (n_cols + kFwdBN - 1) / kFwdBN;
   dim3 grid(row_blocks, chunks);

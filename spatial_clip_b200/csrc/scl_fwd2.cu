@@ -313,9 +313,15 @@ cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorM
                                      float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
                                      cudaStream_t stream) {
   const size_t smem = fwd_pair_smem_bytes(d);
-  cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
   dim3 grid(2 * pairs, chunks);

@@ -63,7 +63,7 @@ if os.environ.get("SCL_CPROFILE") and rank == 0:
     pr.disable()
     torch.cuda.synchronize()
     st = pstats.Stats(pr)
-    st.sort_stats("tottime").print_stats(28)
+    st.sort_stats("cumulative").print_stats(40)
 elif os.environ.get("SCL_CPROFILE"):
     for _ in range(20):
         step()
