@@ -215,7 +215,7 @@ cudaError_t launch_fwd_rowstats(const CUtensorMap& tm_rows, const CUtensorMap& t
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (err != cudaSuccess) return err;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
