@@ -319,6 +319,11 @@ def run_ours(args):
                      "fwd_rowstats_tflops": 2.0 * b_local * N_GLOBAL * D / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
                      "step_algorithmic_tflops_per_gpu": step_alg_tflops,
                      "step_frac_of_burst": step_alg_tflops / pk["burst"],
+                     # executed MMA work of the step: 2 forward passes (2 B_l N D each) + 2 backward passes (similarity
+                     # recompute + gradient GEMM, 4 B_l N D each) = 12 B_l N D per rank -- SURVEY §8d "tensor_pipe_util"
+                     "step_executed_tflops_per_gpu": 2.0 * step_alg_tflops,
+                     "tensor_pipe_util": 2.0 * step_alg_tflops / pk["burst"],
+                     "tensor_pipe_util_of_sustained": 2.0 * step_alg_tflops / pk["sustained"],
                      "executed_tflops": 2.0 * alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
                      "note": "achieved counts the dX GEMM only (algorithmic); the launch also recomputes the similarity "
                              "tile once (executed = 2x)"},

@@ -57,6 +57,10 @@ struct B2Bars {
   uint32_t tmem_base;
 };
 
+// kTune (developer knob SCL_BWD_TUNE, default 0; see profiles/r1_smem_port_accounting.md):
+//   bit 0: column coefficients / G tile through explicit shared-window LDS.128 / STS.128
+//   bit 1: epilogue barrier waits park with a suspend-time hint instead of re-polling every ~100 cycles
+template <int kTune>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
 bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
                      const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
@@ -300,11 +304,21 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     const int diag_col = diag0 + row0 + r_loc;
     const int warp_diag_lo = diag0 + row0 + (q & 1) * 32;
     long long w_cf = 0, w_tf = 0, w_ge = 0;
+    auto epi_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+      if constexpr ((kTune & 2) != 0) {
+        mbar_wait_hint(bar, parity, 4000u);
+        __syncwarp();
+      } else {
+        mbar_wait_warp(bar, parity, timed, acc);
+      }
+    };
+    const uint32_t coef_u32 = smem_u32(smem_coef);
+    const uint32_t g_u32 = smem_u32(smem_g);
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       const uint32_t par = (lt >> 1) & 1;
-      mbar_wait_warp(&bars.coef_full[buf], par, timed, w_cf);
-      mbar_wait_warp(&bars.tmem_full[buf], par, timed, w_tf);
+      epi_wait(&bars.coef_full[buf], par, w_cf);
+      epi_wait(&bars.tmem_full[buf], par, w_tf);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + hh * 32, r);
@@ -320,7 +334,11 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float z = __uint_as_float(r[j + e]);
-          const float4 cc = cf[j + e];  // smem broadcast (same address across the warp)
+          float4 cc;  // smem broadcast (same address across the warp)
+          if constexpr ((kTune & 1) != 0)
+            cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
+          else
+            cc = cf[j + e];
           const float p = ex2_approx(fmaf(z, s2, neg_lr));
           const float pc = ex2_approx(fmaf(z, s2, -cc.x));
           g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
@@ -345,13 +363,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
       }
       // single G buffer: the second GEMM of the previous step must have consumed it
-      mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1, timed, w_ge);
+      epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
       uint8_t* g_row = smem_g + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
-        *reinterpret_cast<uint4*>(g_row + chunk * 16) =
-            make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+        if constexpr ((kTune & 1) != 0)
+          sts_v4(g_u32 + static_cast<uint32_t>(js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128 + chunk * 16),
+                 packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+        else
+          *reinterpret_cast<uint4*>(g_row + chunk * 16) =
+              make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -428,17 +450,20 @@ int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 
-cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
-                                 int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
-                                 const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, long long* dbg_t, cudaStream_t stream) {
+template <int kTune>
+static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols,
+                                          const CUtensorMap& tm_cols_t, int m_rows, int n_cols, int d, int chunks,
+                                          int tiles_per_chunk, int m_pad, int diag0, const float* scale_log2,
+                                          const float4* row_coef, const float4* col_coef, float* dx_partial,
+                                          long long* dbg_t, cudaStream_t stream) {
   const size_t smem = bwd_pair_smem_bytes(d);
   // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    cudaError_t err =
+        cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (err != cudaSuccess) return err;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -446,10 +471,31 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);
   dim3 grid(2 * pairs, chunks, d_slices);
-  bwd_rows_pair_kernel<<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices, n_tiles,
-                                                           tiles_per_chunk, m_pad, diag0, scale_log2, row_coef,
-                                                           col_coef, dx_partial, dbg_t);
+  bwd_rows_pair_kernel<kTune><<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices,
+                                                                  n_tiles, tiles_per_chunk, m_pad, diag0, scale_log2,
+                                                                  row_coef, col_coef, dx_partial, dbg_t);
   return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+                                 int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
+                                 const float* scale_log2, const float4* row_coef, const float4* col_coef,
+                                 float* dx_partial, long long* dbg_t, cudaStream_t stream) {
+  static const int tune = [] {  // developer knob, read once per process
+    const char* e = std::getenv("SCL_BWD_TUNE");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 0;
+  }();
+  switch (tune) {
+    case 1: return launch_bwd_rows_pair_t<1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    case 2: return launch_bwd_rows_pair_t<2>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    case 3: return launch_bwd_rows_pair_t<3>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    default: break;
+  }
+  return launch_bwd_rows_pair_t<0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
+                                   scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
 }
 
 }  // namespace scl

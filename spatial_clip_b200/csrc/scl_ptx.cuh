@@ -60,6 +60,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// try_wait with a suspend-time hint (ns): the thread may stay parked that long before the instruction returns
+// false, so a long wait costs a handful of barrier reads instead of one every ~100 cycles (each try_wait is a
+// shared-memory access; the backward kernel is shared-memory-port bound, profiles/r1_smem_port_accounting.md)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
+    if (++spins > SCL_SPIN_LIMIT) __trap();
+  }
+}
+
 // Warp-level wait: every lane polls (the hardware parks a fully waiting warp), then the warp re-converges.
 // Measured: letting ONE lane poll while 31 sit at the warp barrier is ~2.6x slower for the whole kernel.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
@@ -248,6 +269,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// explicit shared-window vector accesses (one LDS.128 / STS.128 instead of generic LD.E.64 + LD.E pairs)
+__device__ __forceinline__ float4 lds_v4(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 constexpr float kLog2e = 1.4426950408889634f;
