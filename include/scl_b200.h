@@ -21,6 +21,10 @@
  *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16
  *   - feature matrices are row-major [rows, D]; D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 (768, 1024:
  *     CTA-pair kernels only; the backward then runs two D slices and recomputes the similarity tile per slice)
+ *   - fp32-accurate mode ("split", CTA-pair kernels only): operands are bf16 hi/lo pairs laid out by
+ *     scl_split_bf16 as K-concatenated rows of width 3 D -- (h|h|l) for row operands, (h|l|h) for column operands --
+ *     so that the same bf16 tensor-core kernels contract xh.yh + xh.yl + xl.yh; the forward entry points are then
+ *     simply called with d = 3 D, the backward ones with plan.split = 1 and d = D
  */
 #ifndef SCL_B200_H_
 #define SCL_B200_H_
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SCL_ABI_VERSION 3
+#define SCL_ABI_VERSION 4
 #define SCL_OK 0
 #define SCL_ERR_INVALID_ARG (-1)
 #define SCL_ERR_UNSUPPORTED_SHAPE (-2)
@@ -54,16 +58,27 @@ typedef struct scl_plan {
   int n_pad;           /* columns padded to the column tile                         */
   int d_split;         /* bwd: number of D slices (single-CTA: D > 256; CTA-pair: D > 512)  */
   int variant;         /* 0 = single-CTA kernels (cta_group::1), 1 = CTA-pair kernels (cta_group::2) */
+  int split;           /* bwd: 1 = fp32-accurate mode (operands are bf16 hi/lo pairs, see above)      */
 } scl_plan;
 /* variant: 0 / 1 as above, -1 = library default (environment SCL_VARIANT=0|1 overrides the default) */
 int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan);
 int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan);
+/* as scl_bwd_plan with the fp32-accurate mode selectable (split != 0 needs the CTA-pair kernels) */
+int scl_bwd_plan_ex(int m_rows, int n_cols, int d, int variant, int split, scl_plan* plan);
 
 /* ---- HBM-bound producer pass --------------------------------------------------------------------
  * y[rows,d] (bf16) and/or y_t[d,ld_t] (bf16, transposed) from x; normalize != 0 applies
  * F.normalize(x, dim=-1) first (/root/reference/src/open_clip/model.py:326-345). Either output may be NULL. */
 int scl_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t, int normalize,
                   void* stream);
+
+/* fp32-accurate mode: x[rows,d] (any dtype code) -> bf16 pairs h = bf16(x), l = bf16(x - h), written as
+ * rows_out[rows, 3d] = (h|h|l) and/or cols_out[rows, 3d] = (h|l|h) (either may be NULL).  Replaces the same
+ * reference lines as scl_cast_bf16 when float32_logits-grade accuracy (loss rel 1e-5) is wanted. */
+int scl_split_bf16(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d, void* stream);
+/* cols_all[n_rows, 3d] = (h|l|h), the (gathered) column operand -> out_t[2d, ld_t] = [h^T ; l^T], the operand of
+ * the gradient GEMM in the fp32-accurate mode (pad columns n_rows..ld_t-1 are left untouched: pre-zero them) */
+int scl_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, void* stream);
 
 /* scalars[0] = min(logit_scale, cap) (cap <= 0: no cap), [1] = scalars[0]*log2(e), [2] = logit_scale
  * -- forward value of the straight-through cap, losses.py:73-76 */
@@ -163,6 +178,7 @@ typedef struct scl_bwd_args {
   float c, w, mult; int col_mode;
   void* dx_out; int out_dtype;                             /* [b_local, d]                                  */
   void* workspace; size_t workspace_bytes;                 /* >= scl_bwd_workspace_bytes(...)               */
+  int split;                                               /* 1: x_rows [b_local,3d], y_all [n,3d], y_all_t [2d,ld_t] */
 } scl_bwd_args;
 size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int variant);
 int scl_bwd_dir(const scl_bwd_args* a, void* stream);

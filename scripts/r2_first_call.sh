@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round-2 first GPU call (1 GPU, ~12 min): parity of the default kernels, then the opt-in SCL_BWD_TUNE
+# instantiations (parity first, then speed), then the per-role wait-cycle counters -- everything lands in gpurun_out/.
+#   gpurun --timeout 1200 -- 'bash scripts/r2_first_call.sh'
+mkdir -p gpurun_out
+echo "=== default parity"; timeout 400 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/r2_gpu_tests.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2_gpu_tests.log
+for t in 1 2 3; do
+  echo "=== SCL_BWD_TUNE=$t parity (bwd kernels, modules, mid/full size)"
+  SCL_BWD_TUNE=$t timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
+      -k "bwd_rows or modules_match or mid_size or full_size or wide" > gpurun_out/r2_tune${t}_tests.log 2>&1
+  echo "exit $?"; tail -2 gpurun_out/r2_tune${t}_tests.log
+done
+for t in 0 1 2 3; do
+  echo "=== bench SCL_BWD_TUNE=$t"
+  SCL_BWD_TUNE=$t timeout 300 python bench.py --steps 8 --warmup 3 > gpurun_out/r2_bench_tune$t.json 2> gpurun_out/r2_bench_tune$t.err
+  python - <<PY
+import json
+try:
+    j = json.load(open("gpurun_out/r2_bench_tune$t.json")); r = j["roofline"]
+    print("ms/step", round(j["ms_per_step"], 3), "pairs/s", round(j["value"]), "bwd_ms", round(r["launch_ms"], 3),
+          "fwd_ms", round(r["fwd_rowstats_launch_ms"], 3), "loss", j["loss"], "clk", j["clocks"])
+except Exception as e:
+    print("no json", e); print(open("gpurun_out/r2_bench_tune$t.err").read()[-1500:])
+PY
+done
+echo "=== wait-cycle counters (default kernels)"
+timeout 300 python tools/kernel_timing.py > gpurun_out/r2_kernel_timing.txt 2>&1; tail -40 gpurun_out/r2_kernel_timing.txt

@@ -18,7 +18,7 @@ _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 class SclPlan(C.Structure):
     _fields_ = [("chunks", C.c_int), ("tiles_per_chunk", C.c_int), ("n_slots", C.c_int), ("m_pad", C.c_int),
-                ("n_pad", C.c_int), ("d_split", C.c_int), ("variant", C.c_int)]
+                ("n_pad", C.c_int), ("d_split", C.c_int), ("variant", C.c_int), ("split", C.c_int)]
 
 
 class SclError(RuntimeError):
@@ -48,7 +48,8 @@ class BwdArgs(C.Structure):
                 ("d", _I), ("rank", _I), ("variant", _I), ("row_stats", _VP), ("col_stats_all", _VP), ("pos_col", _VP),
                 ("pos_q", _VP), ("opp_q_local", _VP), ("opp_col_all", _VP), ("opp_q_all", _VP), ("k_plus_1", _I),
                 ("gaps", _VP), ("scalars3", _VP), ("grad_out", _VP), ("c", _F), ("w", _F), ("mult", _F),
-                ("col_mode", _I), ("dx_out", _VP), ("out_dtype", _I), ("workspace", _VP), ("workspace_bytes", _SZ)]
+                ("col_mode", _I), ("dx_out", _VP), ("out_dtype", _I), ("workspace", _VP), ("workspace_bytes", _SZ),
+                ("split", _I)]
 
 
 EXPORTS = {
@@ -58,6 +59,9 @@ EXPORTS = {
     "scl_check_device": (C.c_int, [C.POINTER(C.c_int)]),
     "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
     "scl_bwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_bwd_plan_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_split_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "scl_transpose_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "scl_cast_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
     "scl_prep_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
@@ -107,7 +111,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 3:
+    if lib.scl_abi_version() != 4:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -199,10 +203,16 @@ class CudaOps:
         self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, self.variant, C.byref(p)), "scl_fwd_plan")
         return p
 
-    def bwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
+    def bwd_plan(self, m_rows: int, n_cols: int, d: int, split: bool = False) -> SclPlan:
         p = SclPlan()
-        self._check(self.lib.scl_bwd_plan(m_rows, n_cols, d, self.variant, C.byref(p)), "scl_bwd_plan")
+        self._check(self.lib.scl_bwd_plan_ex(m_rows, n_cols, d, self.variant, int(split), C.byref(p)), "scl_bwd_plan")
         return p
+
+    def check_shapes(self, b_local: int, n_global: int, d: int, split: bool, need_backward: bool):
+        """Raise for an unsupported [rows, D] / precision combination before anything is launched."""
+        self.fwd_plan(b_local, n_global, 3 * d if split else d)
+        if need_backward or split:
+            self.bwd_plan(b_local, n_global, d, split)
 
     # ---------------------------------------------------------------- ops
     def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
@@ -218,6 +228,29 @@ class CudaOps:
                                                int(normalize), st), "scl_cast_bf16")
         self.launches += 1
         return y, y_t
+
+    def split_cast(self, x, want_rows=True, want_cols=True):
+        """fp32-accurate mode operands: x [rows, D] -> (h|h|l) and/or (h|l|h) bf16 rows of width 3 D (scl_split_bf16)."""
+        st = self._stream(x)
+        rows, d = x.shape
+        r = self.empty((rows, 3 * d), torch.bfloat16, x) if want_rows else None
+        c = self.empty((rows, 3 * d), torch.bfloat16, x) if want_cols else None
+        with _DeviceGuard(x.device):
+            self._check(self.lib.scl_split_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(r), _ptr(c), rows, d, st),
+                        "scl_split_bf16")
+        self.launches += 1
+        return r, c
+
+    def transpose_split(self, cols_all, d, ld_t):
+        """[N, 3 D] = (h|l|h) -> stacked transposed copy [2 D, ld_t] = [h^T ; l^T] (scl_transpose_split)."""
+        st = self._stream(cols_all)
+        n = cols_all.shape[0]
+        new_t = torch.zeros if ld_t != n else torch.empty
+        out = new_t((2 * d, ld_t), dtype=torch.bfloat16, device=cols_all.device)
+        with _DeviceGuard(cols_all.device):
+            self._check(self.lib.scl_transpose_split(_ptr(cols_all), n, d, ld_t, _ptr(out), st), "scl_transpose_split")
+        self.launches += 1
+        return out
 
     def prep_scalars(self, logit_scale, cap):
         st = self._stream(logit_scale)
@@ -293,12 +326,17 @@ class CudaOps:
         return out
 
     # ---------------------------------------------------------------- composite phases (one host call each)
-    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t):
-        """cap + bf16 casts (+ transposed copies) of both modalities: scl_prepare."""
+    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t, split=False):
+        """cap + bf16 casts (+ transposed copies) of both modalities: scl_prepare.  Returns the row operands, the
+        column operands (the same tensors unless split), the transposed copies (or None) and the scalars."""
         st = self._stream(image)
         rows, d = image.shape
         if text.dtype != image.dtype:
             text = text.to(image.dtype)
+        if split:  # fp32-accurate mode: bf16 hi/lo pairs, K-concatenated (transposed copies are made in backward)
+            img_r, img_c = self.split_cast(image)
+            txt_r, txt_c = self.split_cast(text)
+            return img_r, txt_r, img_c, txt_c, None, None, self.prep_scalars(logit_scale, cap)
         img = self.empty((rows, d), torch.bfloat16, image)
         txt = self.empty((rows, d), torch.bfloat16, image)
         new_t = torch.zeros if ld_t != rows else torch.empty
@@ -311,7 +349,7 @@ class CudaOps:
         with _DeviceGuard(image.device):
             self._check(self.lib.scl_prepare(C.byref(a), st), "scl_prepare")
         self.launches += 3
-        return img, txt, img_t, txt_t, scal
+        return img, txt, img, txt, img_t, txt_t, scal
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
                     finalize_scalars):
@@ -347,15 +385,18 @@ class CudaOps:
         return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4
 
     def backward_dir(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
-                     b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local):
+                     b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local, split=False):
         """dX of the local rows for one direction: scl_bwd_dir (coefficients + fused tensor-core pass + sparse finish).
-        With kernel timing on (bench.py roofline) the three launches are issued separately."""
+        With kernel timing on (bench.py roofline) the three launches are issued separately.
+        split: x_rows [m, 3 D], y_all [n, 3 D], y_all_t [2 D, ld] (fp32-accurate mode); the result is [m, D]."""
         if self.kernel_events is not None or getattr(self, "cycle_buffers", None) is not None:
             return self.bwd_rows(x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype,
-                                 opp_q_local=opp_q_local)
+                                 opp_q_local=opp_q_local, split=split)
         st = self._stream(x_rows)
         m, d = x_rows.shape
+        if split:
+            d //= 3
         n = y_all.shape[0]
         ws_bytes = self.lib.scl_bwd_workspace_bytes(m, n, d, self.variant)
         if ws_bytes == 0:
@@ -365,7 +406,8 @@ class CudaOps:
         a = BwdArgs(_ptr(x_rows), _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], m, n, d, rank, self.variant,
                     _ptr(row_stats), _ptr(col_stats), _ptr(pos_col), _ptr(pos_q), _ptr(opp_q_local),
                     _ptr(opp_col_all), _ptr(opp_q_all), pos_col.shape[1], _ptr(gaps), _ptr(scalars), _ptr(grad_out),
-                    float(c), float(w), float(mult), col_mode, _ptr(out), _DTYPE_CODE[out_dtype], _ptr(ws), ws_bytes)
+                    float(c), float(w), float(mult), col_mode, _ptr(out), _DTYPE_CODE[out_dtype], _ptr(ws), ws_bytes,
+                    int(split))
         with _DeviceGuard(x_rows.device):
             self._check(self.lib.scl_bwd_dir(C.byref(a), st), "scl_bwd_dir")
         self.launches += 3 + (1 if col_mode != 0 else 0) + (1 if out_dtype != torch.float32 else 0)
@@ -396,12 +438,15 @@ class CudaOps:
         return outs
 
     def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
-                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None,
+                 split=False):
         """dX for the local rows: coefficients + fused tensor-core pass + sparse finish."""
         st = self._stream(x_rows)
         m, d = x_rows.shape
+        if split:
+            d //= 3
         n = y_all.shape[0]
-        plan = self.bwd_plan(m, n, d)
+        plan = self.bwd_plan(m, n, d, split)
         row_coef = self.empty((plan.m_pad, 4), torch.float32, x_rows)
         col_coef = self.empty((plan.n_pad, 4), torch.float32, x_rows)
         partial = self.empty((plan.chunks, plan.m_pad, d), torch.float32, x_rows)

@@ -67,11 +67,18 @@ int resolve_variant(int variant) {
   return kDefaultVariant;
 }
 
-// D % 64 == 0 up to 512; 768 and 1024-class widths (D % 256 == 0 up to 1024) run on the CTA-pair kernels only
+// Output width D: D % 64 == 0 up to 512; 768 and 1024-class widths (D % 256 == 0 up to 1024) run on the CTA-pair
+// kernels only (two D slices in the backward).
 bool shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
   if (m_rows < 1 || n_cols < 1 || d < 64) return false;
   if (d <= 512) return d % 64 == 0;
   return variant == 1 && d <= 1024 && d % 256 == 0;
+}
+// Contraction length of the forward pass: as above, plus the K-concatenated operands of the fp32-accurate mode
+// (3 D, so up to 3072) -- beyond 512 the CTA-pair kernel streams X with Y and any multiple of 64 works.
+bool fwd_shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
+  if (m_rows < 1 || n_cols < 1 || d < 64 || d % 64 != 0) return false;
+  return d <= 512 || (variant == 1 && d <= 3072);
 }
 
 }  // namespace
@@ -85,7 +92,8 @@ const char* scl_error_string(int code) {
     case SCL_OK: return "ok";
     case SCL_ERR_INVALID_ARG: return "invalid argument (null / misaligned pointer or bad size)";
     case SCL_ERR_UNSUPPORTED_SHAPE:
-      return "unsupported shape (need rows >= 1 and D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 on the CTA-pair kernels)";
+      return "unsupported shape (need rows >= 1 and D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 on the CTA-pair "
+             "kernels; the fp32-accurate mode needs the CTA-pair kernels)";
     case SCL_ERR_NO_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the CUDA driver";
     case SCL_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled rejected the tensor map";
     case SCL_ERR_NOT_SM100: return "device is not compute capability 10.x (kernels are sm_100a only)";
@@ -109,10 +117,11 @@ int scl_check_device(int* num_sms) {
 
 int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
-  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!fwd_shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0;
   plan->variant = resolve_variant(variant);
-  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  plan->split = 0;
+  if (!fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   if (plan->variant == 1) {
     plan->chunks = scl::fwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
     plan->m_pad = (m_rows + 255) / 256 * 256;
@@ -128,11 +137,17 @@ int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
 }
 
 int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
+  return scl_bwd_plan_ex(m_rows, n_cols, d, variant, 0, plan);
+}
+
+int scl_bwd_plan_ex(int m_rows, int n_cols, int d, int variant, int split, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0, nds = 0, dn = 0;
   plan->variant = resolve_variant(variant);
+  plan->split = split ? 1 : 0;
   if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (plan->split && plan->variant != 1) return SCL_ERR_UNSUPPORTED_SHAPE;
   plan->m_pad = (m_rows + 127) / 128 * 128;
   plan->n_slots = 0;
   if (plan->variant == 1) {
@@ -184,7 +199,7 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
                      void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr)
     return SCL_ERR_INVALID_ARG;
-  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_rows, tm_cols;
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
@@ -250,18 +265,21 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
   scl::bwd_pick_split(d, &nds, &dn);
   CUtensorMap tm_rows, tm_cols, tm_cols_t;
   if (plan->variant == 1) {
-    int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 64);
+    // fp32-accurate mode: x_rows / y_cols are the K-concatenated operands [., 3 d], y_cols_t the stacked [2 d, ld_t]
+    const int kd = plan->split ? 3 * d : d;
+    int rc = make_map(&tm_rows, x_rows, kd, m_rows, kd, 64);
     if (rc != SCL_OK) return rc;
-    rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
+    rc = make_map(&tm_cols, y_cols, kd, n_cols, kd, 128);
     if (rc != SCL_OK) return rc;
-    rc = make_map(&tm_cols_t, y_cols_t, n_cols, d, ld_t, 128);
+    rc = make_map(&tm_cols_t, y_cols_t, n_cols, plan->split ? 2 * d : d, ld_t, 128);
     if (rc != SCL_OK) return rc;
     return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
                                              plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
                                              static_cast<const float4*>(row_coef),
                                              static_cast<const float4*>(col_coef), dx_partial, dbg_cycles,
-                                             static_cast<cudaStream_t>(stream)));
+                                             plan->split, static_cast<cudaStream_t>(stream)));
   }
+  if (plan->split) return SCL_ERR_UNSUPPORTED_SHAPE;
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
   rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
@@ -286,7 +304,7 @@ int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, in
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_bwd_finish(dx_partial, plan->chunks, plan->m_pad, m_rows, d, y_all, pos_col, pos_q,
                                         k_plus_1, opp_col_all, opp_q_all, n_global, b_local, rank, gaps, scalars3,
-                                        grad_out, c, w, mult, col_mode, dx32, dx_out, out_dtype,
+                                        grad_out, c, w, mult, col_mode, plan->split, dx32, dx_out, out_dtype,
                                         static_cast<cudaStream_t>(stream)));
 }
 
@@ -363,7 +381,7 @@ size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int variant) {
 int scl_bwd_dir(const scl_bwd_args* a, void* stream) {
   if (a == nullptr || a->workspace == nullptr || a->dx_out == nullptr) return SCL_ERR_INVALID_ARG;
   scl_plan p;
-  int rc = scl_bwd_plan(a->b_local, a->n_global, a->d, a->variant, &p);
+  int rc = scl_bwd_plan_ex(a->b_local, a->n_global, a->d, a->variant, a->split, &p);
   if (rc != SCL_OK) return rc;
   if (a->workspace_bytes < scl_bwd_workspace_bytes(a->b_local, a->n_global, a->d, a->variant))
     return SCL_ERR_INVALID_ARG;
@@ -385,6 +403,21 @@ int scl_bwd_dir(const scl_bwd_args* a, void* stream) {
   return scl_bwd_finish(partial, &p, a->b_local, a->d, a->y_all, a->pos_col, a->pos_q, a->k_plus_1, a->opp_col_all,
                         a->opp_q_all, a->n_global, a->b_local, a->rank, a->gaps, a->scalars3, a->grad_out, a->c, a->w,
                         a->mult, a->col_mode, dx32, a->dx_out, a->out_dtype, stream);
+}
+
+int scl_split_bf16(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d, void* stream) {
+  if (x == nullptr || (rows_out == nullptr && cols_out == nullptr) || rows < 0 || d <= 0 || d % 64 != 0 ||
+      src_dtype < 0 || src_dtype > 2 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(rows_out) & 15) != 0 || (reinterpret_cast<uintptr_t>(cols_out) & 15) != 0)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_split_cast(x, src_dtype, rows_out, cols_out, rows, d, static_cast<cudaStream_t>(stream)));
+}
+
+int scl_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, void* stream) {
+  if (cols_all == nullptr || out_t == nullptr || n_rows < 0 || d <= 0 || d % 64 != 0 || ld_t < n_rows ||
+      (reinterpret_cast<uintptr_t>(cols_all) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_t) & 15) != 0)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_transpose_split(cols_all, n_rows, d, ld_t, out_t, static_cast<cudaStream_t>(stream)));
 }
 
 int scl_unpack_records(const float* gathered, int world, int rec_floats, int n_comp, float* const* outs,

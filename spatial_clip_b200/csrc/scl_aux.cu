@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
                                                          const float* __restrict__ gaps,
                                                          const float* __restrict__ scalars,
                                                          const float* __restrict__ grad_out, float c, float w,
-                                                         float mult, float* __restrict__ dx32) {
+                                                         float mult, int y_ld, int y_lo,
+                                                         float* __restrict__ dx32) {
+  // y_ld: row pitch of y_all in elements; y_lo >= 0 (fp32-accurate mode): offset of the low-order bf16 part of
+  // every row, added to the high-order part
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= m_rows) return;
@@ -480,9 +483,15 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
       const int col = pos_col[static_cast<size_t>(row) * kp1 + t];
       if (col < 0) continue;
       const float qc = -coef * pos_q[static_cast<size_t>(row) * kp1 + t];
-      const uint2 raw = *reinterpret_cast<const uint2*>(y_all + static_cast<size_t>(col) * d + c0);
-      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      const uint2 raw = *reinterpret_cast<const uint2*>(y_all + static_cast<size_t>(col) * y_ld + c0);
+      float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      if (y_lo >= 0) {
+        const uint2 raw2 = *reinterpret_cast<const uint2*>(y_all + static_cast<size_t>(col) * y_ld + y_lo + c0);
+        const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.x));
+        const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.y));
+        lo.x += lo2.x; lo.y += lo2.y; hi.x += hi2.x; hi.y += hi2.y;
+      }
       acc.x = fmaf(qc, lo.x, acc.x); acc.y = fmaf(qc, lo.y, acc.y);
       acc.z = fmaf(qc, hi.x, acc.z); acc.w = fmaf(qc, hi.y, acc.w);
     }
@@ -499,7 +508,8 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict_
                                                           const float* __restrict__ gaps,
                                                           const float* __restrict__ scalars,
                                                           const float* __restrict__ grad_out, float c, float w,
-                                                          float mult, int col_mode, float* __restrict__ dx32) {
+                                                          float mult, int col_mode, int y_ld, int y_lo,
+                                                          float* __restrict__ dx32) {
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(n_global) * kp1;
   const long long e = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 32 + lane;
@@ -528,9 +538,14 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict_
     const float hq = __shfl_sync(0xffffffffu, qv, src);
     const float qc = base * (s_eff + 2.f * w * gaps[hj / b_local]) * hq;
     float* dst = dx32 + static_cast<size_t>(hc - rank * b_local) * d;
-    const __nv_bfloat16* yrow = y_all + static_cast<size_t>(hj) * d;
+    const __nv_bfloat16* yrow = y_all + static_cast<size_t>(hj) * y_ld;
     for (int c0 = lane * 2; c0 < d; c0 += 64) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + c0));
+      float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + c0));
+      if (y_lo >= 0) {
+        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + y_lo + c0));
+        v.x += v2.x;
+        v.y += v2.y;
+      }
       atomicAdd(dst + c0, qc * v.x);
       atomicAdd(dst + c0 + 1, qc * v.y);
     }
@@ -551,15 +566,18 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                               const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
                               const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                               const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
-                              float* dx32, void* dx_out, int out_dtype, cudaStream_t stream) {
+                              int split, float* dx32, void* dx_out, int out_dtype, cudaStream_t stream) {
   auto yb = static_cast<const __nv_bfloat16*>(y_all);
+  const int y_ld = split ? 3 * d : d;  // split: y_all is the (h | l | h) column operand
+  const int y_lo = split ? d : -1;
   bwd_gather_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(dx_partial, chunks, m_pad, m_rows, d, yb, pos_col, pos_q,
-                                                          kp1, rank, gaps, scalars, grad_out, c, w, mult, dx32);
+                                                          kp1, rank, gaps, scalars, grad_out, c, w, mult, y_ld, y_lo,
+                                                          dx32);
   if (col_mode != 0) {
     const long long entries = static_cast<long long>(n_global) * kp1;
     bwd_scatter_kernel<<<static_cast<unsigned>((entries + 255) / 256), 256, 0, stream>>>(
         opp_col_all, opp_q_all, n_global, kp1, b_local, rank, d, yb, gaps, scalars, grad_out, c, w, mult, col_mode,
-        dx32);
+        y_ld, y_lo, dx32);
   }
   const size_t n = static_cast<size_t>(m_rows) * d;
   if (out_dtype == 1)

@@ -60,7 +60,11 @@ struct B2Bars {
 // kTune (developer knob SCL_BWD_TUNE, default 0; see profiles/r1_smem_port_accounting.md):
 //   bit 0: column coefficients / G tile through explicit shared-window LDS.128 / STS.128
 //   bit 1: epilogue barrier waits park with a suspend-time hint instead of re-polling every ~100 cycles
-template <int kTune>
+// kSplit = 1 is the fp32-accurate ("bf16x2") mode: every operand is a bf16 hi + lo pair.  The similarity is
+// contracted over the K-concatenated rows X' = (h|h|l), Y' = (h|l|h) of width 3 d (x.y ~= xh.yh + xh.yl + xl.yh,
+// the dropped terms are O(2^-18)), G is written as two bf16 tiles G1 + G2 and the gradient GEMM runs three passes
+// G1.Yh + G1.Yl + G2.Yh against the stacked transposed copy [Yh^T ; Yl^T] ([2 d, ld]).  X is always streamed.
+template <int kTune, int kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
 bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
                      const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
@@ -76,16 +80,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
                           : nullptr;
   const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nk = d / kB2BK;
+  const int nk = (kSplit ? 3 * d : d) / kB2BK;  // K chunks of the similarity contraction
   // D <= 512: one D slice, X block resident.  D > 512 (TMEM cannot hold dX[64 x D]): blockIdx.z selects a
   // slice of ds = D / d_slices output columns; z is still contracted over all of D, with the X chunks
   // streamed through the ring next to the Y chunks.
-  const bool stream_x = d_slices > 1;
+  const bool stream_x = kSplit != 0 || d_slices > 1;
   const int ds = d / d_slices;
   const int d0 = static_cast<int>(blockIdx.z) * ds;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary (absent when streamed)
   uint8_t* smem_g = smem_x + (stream_x ? 0 : nk * kB2XChunkBytes);  // 32 KB, single buffer
-  uint8_t* smem_ring = smem_g + kB2GBytes;               // 3 x 32 KB
+  uint8_t* smem_g2 = smem_g + kB2GBytes;                 // split mode only: the low-order tile G2
+  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // 3 x 32 KB
   uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (ds + 255) / 256;  // accumulator groups of up to 256 output columns
@@ -177,14 +182,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       auto push_yt = [&](int lt) {
         const int col0 = (t_begin + lt) * kB2TileN;
         const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
-        for (int u = 0; u < n_units; u += 2) {
-          const int nb = min(2, n_units - u);
-          const int s = acquire(nb * kB2SlotBytes);
-          for (int b = 0; b < nb; ++b) {
-            const int js = (u + b) / ng, g = (u + b) % ng;
-            const int n_g = min(256, ds - 256 * g);
-            tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
-                             col0 + js * 64, d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
+        for (int p = 0; p < (kSplit ? 3 : 1); ++p) {  // split passes: (G1, Yh^T), (G1, Yl^T), (G2, Yh^T)
+          const int t_row0 = (p == 1) ? d : 0;        // Yl^T is stacked below Yh^T
+          for (int u = 0; u < n_units; u += 2) {
+            const int nb = min(2, n_units - u);
+            const int s = acquire(nb * kB2SlotBytes);
+            for (int b = 0; b < nb; ++b) {
+              const int js = (u + b) / ng, g = (u + b) % ng;
+              const int n_g = min(256, ds - 256 * g);
+              tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
+                               col0 + js * 64, t_row0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
+            }
           }
         }
       };
@@ -248,27 +256,31 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         mbar_wait_warp(&bars.g_full, lt & 1, timed, w_gf);
         tc_fence_after();
         const int n_units = 4 * ng;
-        for (int u = 0; u < n_units; u += 2, advance()) {
-          const int nb = min(2, n_units - u);
-          const int s = ring_s;
-          mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fy);
-          tc_fence_after();
-          if (elect_one()) {
-            for (int b = 0; b < nb; ++b) {
-              const int js = (u + b) / ng, g = (u + b) % ng;
-              const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g));
-              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_g + js * kB2GSubBytes));
-              const uint64_t b_desc =
-                  umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
+        constexpr int n_pass = kSplit ? 3 : 1;
+        for (int p = 0; p < n_pass; ++p) {
+          const uint8_t* g_tile = (kSplit && p == 2) ? smem_g2 : smem_g;
+          for (int u = 0; u < n_units; u += 2, advance()) {
+            const int nb = min(2, n_units - u);
+            const int s = ring_s;
+            mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fy);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int b = 0; b < nb; ++b) {
+                const int js = (u + b) / ng, g = (u + b) % ng;
+                const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g));
+                const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(g_tile + js * kB2GSubBytes));
+                const uint64_t b_desc =
+                    umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_acc,
-                                 (lt | js | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_acc,
+                                   (lt | p | js | k) != 0 ? 1u : 0u);
+              }
+              tc_commit_pair(&bars.empty[s]);
+              if (p == n_pass - 1 && u + nb >= n_units) tc_commit_pair(&bars.g_empty);
             }
-            tc_commit_pair(&bars.empty[s]);
-            if (u + nb >= n_units) tc_commit_pair(&bars.g_empty);
+            __syncwarp();
           }
-          __syncwarp();
         }
       };
       issue_z(0);
@@ -327,53 +339,100 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
       const bool ragged = col0 + 32 > n_cols;                                           // warp-uniform
       tmem_ld_wait();
-      uint32_t packed[16];
+      if constexpr (kSplit != 0) {
+        // fp32-accurate mode: G = G1 + G2 (two bf16 tiles).  z already sits in registers, so TMEM goes back first;
+        // the arithmetic then runs 8 columns at a time straight into the two 16-byte stores (low register pressure;
+        // the step is dominated by its 3x MMA work, so not overlapping the math with the g_empty wait costs nothing).
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&bars.tmem_empty[buf]);
+          else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
+        }
+        epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
+        const int g_off = js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float g2[2];
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float z = __uint_as_float(r[j + e]);
-          float4 cc;  // smem broadcast (same address across the warp)
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = ch * 8 + jj * 2;
+            float g2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float z = __uint_as_float(r[j + e]);
+              const float4 cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
+              const float p = ex2_approx(fmaf(z, s2, neg_lr));
+              const float pc = ex2_approx(fmaf(z, s2, -cc.x));
+              g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
+            }
+            if (has_diag) {
+              const int di = diag_col - col0;
+              g2[0] -= (j == di) ? rc.w : 0.f;
+              g2[1] -= (j + 1 == di) ? rc.w : 0.f;
+            }
+            if (ragged) {
+              g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
+              g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
+            }
+            hi[jj] = pack_bf16x2(g2[0], g2[1]);
+            lo[jj] = pack_bf16x2(g2[0] - __uint_as_float(hi[jj] << 16), g2[1] - __uint_as_float(hi[jj] & 0xffff0000u));
+          }
+          const uint32_t off = static_cast<uint32_t>(g_off + (((c16 + ch) ^ (r_loc & 7)) * 16));
+          sts_v4(g_u32 + off, hi[0], hi[1], hi[2], hi[3]);
+          sts_v4(g_u32 + kB2GBytes + off, lo[0], lo[1], lo[2], lo[3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.coef_empty[buf]);
+      } else {
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float g2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float z = __uint_as_float(r[j + e]);
+            float4 cc;  // smem broadcast (same address across the warp)
+            if constexpr ((kTune & 1) != 0)
+              cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
+            else
+              cc = cf[j + e];
+            const float p = ex2_approx(fmaf(z, s2, neg_lr));
+            const float pc = ex2_approx(fmaf(z, s2, -cc.x));
+            g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
+          }
+          if (has_diag) {
+            const int di = diag_col - col0;
+            g2[0] -= (j == di) ? rc.w : 0.f;
+            g2[1] -= (j + 1 == di) ? rc.w : 0.f;
+          }
+          if (ragged) {
+            g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
+            g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
+          }
+          packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
+        }
+        // z is in registers now: hand the TMEM buffer back before the (possibly waiting) G write
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars.coef_empty[buf]);
+          if (leader) mbar_arrive(&bars.tmem_empty[buf]);
+          else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
+        }
+        // single G buffer: the second GEMM of the previous step must have consumed it
+        epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
+        uint8_t* g_row = smem_g + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
           if constexpr ((kTune & 1) != 0)
-            cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
+            sts_v4(g_u32 + static_cast<uint32_t>(js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128 + chunk * 16),
+                   packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
           else
-            cc = cf[j + e];
-          const float p = ex2_approx(fmaf(z, s2, neg_lr));
-          const float pc = ex2_approx(fmaf(z, s2, -cc.x));
-          g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
+            *reinterpret_cast<uint4*>(g_row + chunk * 16) =
+                make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
         }
-        if (has_diag) {
-          const int di = diag_col - col0;
-          g2[0] -= (j == di) ? rc.w : 0.f;
-          g2[1] -= (j + 1 == di) ? rc.w : 0.f;
-        }
-        if (ragged) {
-          g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
-          g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
-        }
-        packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
-      }
-      // z is in registers now: hand the TMEM buffer back before the (possibly waiting) G write
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bars.coef_empty[buf]);
-        if (leader) mbar_arrive(&bars.tmem_empty[buf]);
-        else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
-      }
-      // single G buffer: the second GEMM of the previous step must have consumed it
-      epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
-      uint8_t* g_row = smem_g + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
-        if constexpr ((kTune & 1) != 0)
-          sts_v4(g_u32 + static_cast<uint32_t>(js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128 + chunk * 16),
-                 packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-        else
-          *reinterpret_cast<uint4*>(g_row + chunk * 16) =
-              make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -417,9 +476,9 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
 
 int bwd_pair_d_slices(int d) { return d > 512 ? 2 : 1; }
 
-size_t bwd_pair_smem_bytes(int d) {
-  const size_t x_block = d > 512 ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
-  return 1024 + x_block + kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
+size_t bwd_pair_smem_bytes(int d, int split) {
+  const size_t x_block = (split || d > 512) ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
+  return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
 }
 
 // Column chunking for a grid of `units` row blocks (CTAs or CTA pairs) over `slots` concurrently resident
@@ -450,20 +509,20 @@ int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 
-template <int kTune>
+template <int kTune, int kSplit>
 static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols,
                                           const CUtensorMap& tm_cols_t, int m_rows, int n_cols, int d, int chunks,
                                           int tiles_per_chunk, int m_pad, int diag0, const float* scale_log2,
                                           const float4* row_coef, const float4* col_coef, float* dx_partial,
                                           long long* dbg_t, cudaStream_t stream) {
-  const size_t smem = bwd_pair_smem_bytes(d);
+  const size_t smem = bwd_pair_smem_bytes(d, kSplit);
   // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err =
-        cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune, kSplit>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (err != cudaSuccess) return err;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -471,30 +530,33 @@ static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUte
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);
   dim3 grid(2 * pairs, chunks, d_slices);
-  bwd_rows_pair_kernel<kTune><<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices,
-                                                                  n_tiles, tiles_per_chunk, m_pad, diag0, scale_log2,
-                                                                  row_coef, col_coef, dx_partial, dbg_t);
+  bwd_rows_pair_kernel<kTune, kSplit><<<grid, kB2Threads, smem, stream>>>(
+      tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices, n_tiles, tiles_per_chunk, m_pad, diag0, scale_log2,
+      row_coef, col_coef, dx_partial, dbg_t);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, long long* dbg_t, cudaStream_t stream) {
+                                 float* dx_partial, long long* dbg_t, int split, cudaStream_t stream) {
+  if (split)
+    return launch_bwd_rows_pair_t<0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                        diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
   static const int tune = [] {  // developer knob, read once per process
     const char* e = std::getenv("SCL_BWD_TUNE");
     return (e != nullptr && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 0;
   }();
   switch (tune) {
-    case 1: return launch_bwd_rows_pair_t<1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 1: return launch_bwd_rows_pair_t<1, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 2: return launch_bwd_rows_pair_t<2>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 2: return launch_bwd_rows_pair_t<2, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 3: return launch_bwd_rows_pair_t<3>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 3: return launch_bwd_rows_pair_t<3, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
     default: break;
   }
-  return launch_bwd_rows_pair_t<0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
+  return launch_bwd_rows_pair_t<0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
                                    scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
 }
 

@@ -29,13 +29,13 @@ cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorM
                                      int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
                                      float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
                                      cudaStream_t stream);
-size_t bwd_pair_smem_bytes(int d);
+size_t bwd_pair_smem_bytes(int d, int split);
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
 int bwd_pair_d_slices(int d);
 cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, long long* dbg_t, cudaStream_t stream);
+                                 float* dx_partial, long long* dbg_t, int split, cudaStream_t stream);
 
 // ---- HBM-bound side passes (scl_aux.cu)
 cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t,
@@ -62,7 +62,12 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                               const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
                               const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                               const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
-                              float* dx32, void* dx_out, int out_dtype, cudaStream_t stream);
+                              int split, float* dx32, void* dx_out, int out_dtype, cudaStream_t stream);
+
+// ---- fp32-accurate ("bf16x2") operand preparation (scl_split.cu)
+cudaError_t launch_split_cast(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d,
+                              cudaStream_t stream);
+cudaError_t launch_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, cudaStream_t stream);
 
 cudaError_t launch_unpack_records(const float* in, int world, int rec_floats, int n_comp, float* const* outs,
                                   const int* offs, const int* lens, cudaStream_t stream);

@@ -25,7 +25,8 @@ What differs from the reference, by design:
     ``world_size=1`` to reproduce that quirk);
   * a scalar ``logit_bias`` cancels in both softmaxes and is ignored (zero gradient);
   * arithmetic: bf16 operands, fp32 accumulation / logits / statistics on chip ("float32_logits" is
-    always on).
+    always on); the extra constructor keyword ``precision="fp32"`` switches to bf16 hi/lo operand pairs
+    (three tensor-core products per GEMM) for fp32-grade results.
 
 The modules hold no parameters and no buffers (checkpoints stay interchangeable).
 No CPU fallback exists: without libscl_b200.so, or with CPU tensors, ``forward`` raises.
@@ -92,6 +93,7 @@ class _Cfg:
     temp_reg_weight: float
     alpha_scale: float
     group: object = None
+    split: bool = False  # fp32-accurate mode: operands carried as bf16 hi/lo pairs
 
 
 def _col_mode(cfg: _Cfg) -> int:
@@ -118,19 +120,23 @@ class _ContrastiveLossFn(torch.autograd.Function):
         dev = image_features.device
 
         scale = logit_scale.detach().reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous()
+        if hasattr(ops, "check_shapes"):
+            ops.check_shapes(b_local, n, d, cfg.split, any(ctx.needs_input_grad[:2]))
 
         # ---- cap, bf16 copies (gather_features operands, loss.py:21-65).  Single rank + backward wanted: the
         # transposed copies the backward GEMMs need come out of the same pass (dImage needs text^T and vice versa)
         ld_t = (n + 7) // 8 * 8
         fuse_t = world == 1  # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
-        img_l, txt_l, img_t, txt_t, scalars = ops.prepare(
+        # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
+        # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
+        img_l, txt_l, img_c, txt_c, img_t, txt_t, scalars = ops.prepare(
             image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap,
-            fuse_t and ctx.needs_input_grad[1], fuse_t and ctx.needs_input_grad[0], ld_t)
+            fuse_t and ctx.needs_input_grad[1], fuse_t and ctx.needs_input_grad[0], ld_t, split=cfg.split)
         if world > 1:
-            img_all = _all_gather_rows(img_l, world, cfg.group)
-            txt_all = _all_gather_rows(txt_l, world, cfg.group)
+            img_all = _all_gather_rows(img_c, world, cfg.group)
+            txt_all = _all_gather_rows(txt_c, world, cfg.group)
         else:
-            img_all, txt_all = img_l, txt_l
+            img_all, txt_all = img_c, txt_c
 
         # ---- tile ids (losses.py:63-68); plain CLIP has only the diagonal
         ids = None
@@ -162,6 +168,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
             out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
 
         ctx.cfg = cfg
+        ctx.d = d
         ctx.c = c
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
         ctx.scale_shape = logit_scale.shape
@@ -177,7 +184,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         cfg: _Cfg = ctx.cfg
         (img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti, q_ti) = ctx.saved_tensors
         world, rank = cfg.world, cfg.rank
-        b_local, d = img_l.shape
+        b_local, d = img_l.shape[0], ctx.d
         n = world * b_local
         go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
 
@@ -203,16 +210,18 @@ class _ContrastiveLossFn(torch.autograd.Function):
         img_all_t, txt_all_t = ctx.transposed
         if need_i:
             if txt_all_t is None:
-                _, txt_all_t = ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)
+                txt_all_t = ops.transpose_split(txt_all, d, ld_t) if cfg.split else \
+                    ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
             d_img = ops.backward_dir(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all,
                                      q_ti_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
-                                     ctx.in_dtypes[0], q_ti)
+                                     ctx.in_dtypes[0], q_ti, split=cfg.split)
         if need_t:
             if img_all_t is None:
-                _, img_all_t = ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)
+                img_all_t = ops.transpose_split(img_all, d, ld_t) if cfg.split else \
+                    ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
             d_txt = ops.backward_dir(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all,
                                      q_it_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
-                                     ctx.in_dtypes[1], q_it)
+                                     ctx.in_dtypes[1], q_it, split=cfg.split)
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)
@@ -223,10 +232,16 @@ class _ContrastiveLossFn(torch.autograd.Function):
 # modules
 # ------------------------------------------------------------------------------------------------
 class _LossBase(nn.Module):
-    def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod):
+    def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod, precision="bf16"):
         super().__init__()
         if use_horovod:
             raise NotImplementedError("horovod exchange is out of scope; use torch.distributed (NCCL)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        # "bf16": operands rounded to bf16 (loss rel 1e-3, grads 3e-2 of max vs the fp32 reference).
+        # "fp32": operands carried as bf16 hi/lo pairs, three tensor-core products per GEMM, dL/dz as two bf16 tiles
+        #         (loss rel 1e-5, grads 1e-4 of max vs the fp32 reference; ~3x the tensor work; CTA-pair kernels)
+        self.precision = precision
         self.local_loss = bool(local_loss)
         self.gather_with_grad = bool(gather_with_grad)
         self.use_horovod = False
@@ -268,8 +283,8 @@ class SpatialLoss(_LossBase):
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, rank: Optional[int] = None,
                  world_size: Optional[int] = None, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
-                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod)
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16"):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision)
         self.cap_logit_scale = cap_logit_scale
         self.temp_reg_weight = float(temp_reg_weight or 0.0)
         self.float32_logits = float32_logits  # logits are always fp32 on chip
@@ -287,7 +302,8 @@ class SpatialLoss(_LossBase):
                 text_tile_ids.shape[0] != b:
             raise ValueError("tile ids must be [B] and neighbour ids / alphas [B, K]")
         cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
-                   self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group)
+                   self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
+                   self.precision == "fp32")
         loss, col, w, q = _ContrastiveLossFn.apply(image_features, text_features,
                                                    self._scale_tensor(logit_scale, image_features), image_tile_ids,
                                                    text_tile_ids, neighbor_tile_ids, neighbor_alphas, cfg)
@@ -299,15 +315,16 @@ class ClipLoss(_LossBase):
     """Symmetric InfoNCE (reference: losses.py:126-141 wrapping open_clip loss.py:68-155)."""
 
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, use_horovod: bool = False):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod)
+                 rank: Optional[int] = None, world_size: Optional[int] = None, use_horovod: bool = False,
+                 precision: str = "bf16"):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision)
         self.cache_labels = cache_labels  # labels are implicit (the diagonal); nothing to cache
 
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
                 logit_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self._check_features(image_features, text_features, logit_bias)
         cfg = _Cfg("clip", self.rank, self.world_size, self.local_loss, self.gather_with_grad, None, 0.0, 1.0,
-                   self.process_group)
+                   self.process_group, self.precision == "fp32")
         loss, _, _, _ = _ContrastiveLossFn.apply(image_features, text_features,
                                                  self._scale_tensor(logit_scale, image_features), None, None, None,
                                                  None, cfg)
@@ -320,9 +337,9 @@ class GlobalMappingMultiPositiveClipLoss(SpatialLoss):
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
                  rank: Optional[int] = 0, world_size: Optional[int] = 1, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
-                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0):
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16"):
         super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, cap_logit_scale,
-                         temp_reg_weight, float32_logits, neighbor_alpha_scale)
+                         temp_reg_weight, float32_logits, neighbor_alpha_scale, precision)
         self.cache_labels = cache_labels
 
     def forward(self, image_features, text_features, image_tile_ids, text_tile_ids, neighbor_tile_ids,

@@ -101,10 +101,23 @@ class EmulatedOps:
         return torch.stack([loss, gap, ds, 2 * w * gap]).float()
 
     # ---- composite phases, assembled from the per-op contracts above
-    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t):
-        img, img_t = self.cast_bf16(image, want_t=want_img_t, ld_t=ld_t)
-        txt, txt_t = self.cast_bf16(text, want_t=want_txt_t, ld_t=ld_t)
-        return img, txt, img_t, txt_t, self.prep_scalars(logit_scale, cap)
+    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t, split=False):
+        # split (the fp32-accurate mode): the checker keeps the unrounded values in one [rows, D] tensor -- the
+        # hi/lo layout is a device detail; what the host logic must get right is which tensor goes where
+        self.calls.append("prepare_split" if split else "prepare")
+        rb, self.round_bf16 = self.round_bf16, self.round_bf16 and not split
+        try:
+            img, img_t = self.cast_bf16(image, want_t=want_img_t and not split, ld_t=ld_t)
+            txt, txt_t = self.cast_bf16(text, want_t=want_txt_t and not split, ld_t=ld_t)
+        finally:
+            self.round_bf16 = rb
+        return img, txt, img, txt, img_t, txt_t, self.prep_scalars(logit_scale, cap)
+
+    def transpose_split(self, cols_all, d, ld_t):
+        self.calls.append("transpose_split")
+        y_t = torch.zeros(d, ld_t, dtype=cols_all.dtype)
+        y_t[:, : cols_all.shape[0]] = cols_all.t()
+        return y_t
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
                     finalize_scalars):
@@ -122,7 +135,7 @@ class EmulatedOps:
         out4 = self.loss_scalars(sums6, scalars, c, w) if finalize_scalars else None
         return it, ti, stats_i, stats_t, sums6, out4
 
-    def backward_dir(self, *args):
+    def backward_dir(self, *args, split=False):
         return self.bwd_rows(*args[:-1], opp_q_local=args[-1])
 
     def exchange_records(self, parts, world, gather_fn):

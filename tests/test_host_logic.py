@@ -71,6 +71,27 @@ def test_single_rank_modules_match_reference(name, emulated):
     _assert_close(gold, 0, meta["gen"]["n"], loss, gi, gt, ds, meta["scale"])
 
 
+@pytest.mark.parametrize("name", ["spatial_n64_k8_default", "spatial_n96_edges", "clip_n300_d256"])
+def test_fp32_precision_routes_split_operands(name):
+    """precision="fp32": the operands come from the split path (prepare(split=True), transposed copies from
+    transpose_split in backward) and the results meet the fp32 gate against the reference goldens."""
+    ops = EmulatedOps(round_bf16=True)  # rounding must be bypassed by the split route
+    prev = losses._set_ops_for_testing(ops)
+    try:
+        meta, gold = load_golden(name)
+        c = dict(meta["ctor"], precision="fp32")
+        c.pop("cache_labels", None) if meta["kind"] == "spatial" else None
+        mod = SpatialLoss(**c) if meta["kind"] == "spatial" else ClipLoss(**c)
+        loss, gi, gt, ds = _run_rank(meta, 0, 1, mod)
+        _assert_close(gold, 0, meta["gen"]["n"], loss, gi, gt, ds, meta["scale"])
+        assert "prepare_split" in ops.calls and ops.calls.count("transpose_split") == 2
+        assert "prepare" not in ops.calls
+    finally:
+        losses._set_ops_for_testing(prev)
+    with pytest.raises(ValueError):
+        ClipLoss(precision="fp64")
+
+
 def test_legacy_positional_order(emulated):
     meta, gold = load_golden("legacy_n64_k8_default")
     b = make_spot_batch(**meta["gen"])
