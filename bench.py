@@ -178,7 +178,8 @@ def run_ours(args):
                 alpha=loc.neighbor_alphas.pin_memory())
     dev_in = {k: v.to(dev) for k, v in host.items()}
     scale = torch.tensor(SCALE, device=dev, requires_grad=True)
-    mod = SpatialLoss(**SPATIAL_CFG)
+    mod = SpatialLoss(**SPATIAL_CFG, precision=args.precision)
+    split = args.precision == "fp32"
     ops = losses._ops()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -280,12 +281,17 @@ def run_ours(args):
     ev = kernel_events.get("bwd_rows", [])
     k_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
     alg_flops_launch = 2.0 * b_local * N_GLOBAL * D  # the dX GEMM; the z recompute is not algorithmic work
+    mma_factor = 3.0 if split else 1.0  # fp32-accurate mode: three bf16 products per algorithmic one
     achieved = alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     # forward pass kernel, timed on its own after the step loop (inside the step it is part of one composite call).
     # RANK 0 ONLY from here on: no collectives below -- the column operand is a local stand-in of the right shape
     # (kernel time does not depend on the values).
-    xb, _ = ops.cast_bf16(dev_in["img"])
-    yb = xb.repeat(world, 1) if world > 1 else xb
+    if split:
+        xb, yb = ops.split_cast(dev_in["img"])
+    else:
+        xb, _ = ops.cast_bf16(dev_in["img"])
+        yb = xb
+    yb = yb.repeat(world, 1) if world > 1 else yb
     sc3 = ops.prep_scalars(torch.tensor([SPATIAL_CFG["cap_logit_scale"]], device=dev), None)
     ops.kernel_events = {}
     for _ in range(4):
@@ -302,8 +308,9 @@ def run_ours(args):
     line = {
         "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
         "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": workload_config(world),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16x2 (fp32-accurate: bf16 hi/lo operand pairs, fp32 accumulate)" if split else "bf16",
+        "data": "synthetic", "config": {**workload_config(world), "precision": args.precision},
         "pairs_per_s_per_gpu": pairs_per_s / world,
         "loss": loss_val,
         "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
@@ -321,10 +328,10 @@ def run_ours(args):
                      "step_frac_of_burst": step_alg_tflops / pk["burst"],
                      # executed MMA work of the step: 2 forward passes (2 B_l N D each) + 2 backward passes (similarity
                      # recompute + gradient GEMM, 4 B_l N D each) = 12 B_l N D per rank -- SURVEY §8d "tensor_pipe_util"
-                     "step_executed_tflops_per_gpu": 2.0 * step_alg_tflops,
-                     "tensor_pipe_util": 2.0 * step_alg_tflops / pk["burst"],
-                     "tensor_pipe_util_of_sustained": 2.0 * step_alg_tflops / pk["sustained"],
-                     "executed_tflops": 2.0 * alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
+                     "step_executed_tflops_per_gpu": 2.0 * mma_factor * step_alg_tflops,
+                     "tensor_pipe_util": 2.0 * mma_factor * step_alg_tflops / pk["burst"],
+                     "tensor_pipe_util_of_sustained": 2.0 * mma_factor * step_alg_tflops / pk["sustained"],
+                     "executed_tflops": 2.0 * mma_factor * alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
                      "note": "achieved counts the dX GEMM only (algorithmic); the launch also recomputes the similarity "
                              "tile once (executed = 2x)"},
         "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -342,6 +349,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
+                    help="fp32: the fp32-accurate mode (bf16 hi/lo operand pairs), BASELINE configs[4]'s 'fp32 vs bf16'")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,3 +59,33 @@ def test_plans_and_errors_without_gpu(lib):
     assert lib.scl_fwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
     assert p.variant == 1 and p.m_pad == 512
     assert lib.scl_positives_workspace_bytes(1000) >= 2048 * 12
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every argument struct as gcc sees include/scl_b200.h == the ctypes mirror in _cuda.py."""
+    import shutil
+    import subprocess
+
+    from spatial_clip_b200 import _cuda
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    mirrors = {"scl_plan": _cuda.SclPlan, "scl_prepare_args": _cuda.PrepareArgs, "scl_fwd_args": _cuda.FwdArgs,
+               "scl_bwd_args": _cuda.BwdArgs}
+    lines = []
+    for cname, cls in mirrors.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void) {\n%s\nreturn 0;\n}\n'
+                   % (ROOT / "include/scl_b200.h", "\n".join(lines)))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
