@@ -193,3 +193,76 @@ class EmulatedOps:
                 coefj = g * (s_eff + k2c[idx]) * opp_q_all[idx, t].double()
                 dx.index_add_(0, cc[idx] - lo, -(coefj[:, None] * yd[idx]))
         return dx.to(out_dtype)
+
+
+def _split2(x):
+    h = x.float().bfloat16().float()
+    return h, (x.float() - h).bfloat16().float()
+
+
+class SplitArithmeticOps(EmulatedOps):
+    """TEST-ONLY: the ARITHMETIC of the fp32-accurate device mode, restated on the CPU in fp32 -- operands as bf16
+    hi/lo pairs, z = xh.yh + xh.yl + xl.yh, dL/dz split into two bf16 tiles, dX = G1.Yh + G1.Yl + G2.Yh -- so the
+    error budget of that scheme can be pinned against the reference goldens without a GPU
+    (tests/test_fp32_mode_numerics.py)."""
+    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
+        y = x.float().clone(); y_t = None
+        if want_t:
+            y_t = torch.zeros(x.shape[1], ld_t); y_t[:, :x.shape[0]] = y.t()
+        return (y if want_rows else None), y_t
+    def _z(self, x, y):
+        xh, xl = _split2(x); yh, yl = _split2(y)
+        return (xh @ yh.t() + xh @ yl.t() + xl @ yh.t())   # fp32
+    def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
+        z = self._z(x_rows, y_cols)
+        y2 = z * float(scalars[1])
+        m = y2.max(dim=1).values
+        e = torch.exp2(y2 - m[:, None])
+        part = torch.stack([m, e.sum(1), (e * z).sum(1), (e * z * z).sum(1)], dim=1).float()
+        return part, SimpleNamespace(n_slots=1, m_pad=x_rows.shape[0])
+    def row_finalize(self, partial, plan, x_rows, y_all, pos_col, pos_q):
+        m, s0, s1, s2 = partial.float().unbind(1)
+        mu = s1 / s0; var = s2 / s0 - mu * mu
+        zq = torch.zeros_like(mu)
+        xh, xl = _split2(x_rows); yh, yl = _split2(y_all)
+        for t in range(pos_col.shape[1]):
+            c = pos_col[:, t].long(); ok = c >= 0; cc = c.clamp(min=0)
+            zz = (xh * yh[cc]).sum(1) + (xh * yl[cc]).sum(1) + (xl * yh[cc]).sum(1)
+            zq += torch.where(ok, pos_q[:, t] * zz, torch.zeros_like(zz))
+        return torch.stack([m + torch.log2(s0), mu, var, zq], dim=1).float()
+    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+                 b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
+        m, d = x_rows.shape; n = y_all.shape[0]
+        s_eff, s2 = float(scalars[0]), float(scalars[1])
+        g = float(grad_out[0]) * mult * c
+        z = self._z(x_rows, y_all)
+        rs, cs = row_stats.float(), col_stats.float(); gaps = gaps.float()
+        k2r = 2 * w * gaps[rank]
+        u = g * (s_eff + k2r * (1 - s_eff * rs[:, 1])); v = g * k2r * s_eff * torch.ones(m)
+        owner = torch.arange(n) // b_local
+        on = torch.ones(n) if col_mode == 2 else ((owner == rank).float() if col_mode == 1 else torch.zeros(n))
+        k2c = 2 * w * gaps[owner]
+        uc = on * g * (s_eff + k2c * (1 - s_eff * cs[:, 1])); vc = on * g * k2c * s_eff
+        p = torch.exp2(z * s2 - rs[:, 0:1]); pc = torch.exp2(z * s2 - cs[None, :, 0])
+        G = p * (u[:, None] + v[:, None] * z) + pc * (uc[None, :] + vc[None, :] * z)
+        # own-column term subtracted before rounding (as the kernel does)
+        qd = pos_q[:, 0].float() + (opp_q_local[:, 0].float() if col_mode != 0 else 0)
+        tdiag = g * (s_eff + k2r) * qd
+        idx = torch.arange(m); G[idx, rank * b_local + idx] -= tdiag
+        G1, G2 = _split2(G); yh, yl = _split2(y_all)
+        dx = G1 @ yh + G1 @ yl + G2 @ yh
+        yd = yh + yl
+        coef = g * (s_eff + k2r)
+        for t in range(1, pos_col.shape[1]):
+            cc = pos_col[:, t].long(); ok = (cc >= 0).float()
+            dx -= (coef * ok * pos_q[:, t])[:, None] * yd[cc.clamp(min=0)]
+        if col_mode != 0:
+            lo, hi = rank * b_local, (rank + 1) * b_local
+            for t in range(1, opp_col_all.shape[1]):
+                cc = opp_col_all[:, t].long(); sel = (cc >= lo) & (cc < hi)
+                if col_mode == 1: sel &= owner == rank
+                ix = torch.nonzero(sel).squeeze(1)
+                if ix.numel() == 0: continue
+                coefj = g * (s_eff + k2c[ix]) * opp_q_all[ix, t]
+                dx.index_add_(0, cc[ix] - lo, -(coefj[:, None] * yd[ix]))
+        return dx.to(out_dtype)
