@@ -27,5 +27,8 @@ echo "=== fp32-accurate mode (precision=fp32): parity, then speed"
 SCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_fp32_mode.py -m gpu -q -p no:cacheprovider -s > gpurun_out/r2_fp32_tests.log 2>&1
 echo "exit $?"; grep -E "passed|failed" gpurun_out/r2_fp32_tests.log | tail -2; grep -E "^(FAILED|ERROR|E  +Assert|E  +assert|E  +.*Error)" gpurun_out/r2_fp32_tests.log | cut -c1-240 | head -20
 timeout 300 python bench.py --steps 5 --warmup 3 --precision fp32 > gpurun_out/r2_bench_fp32.json 2> gpurun_out/r2_bench_fp32.err; echo "exit $?"; tail -c 600 gpurun_out/r2_bench_fp32.json; tail -3 gpurun_out/r2_bench_fp32.err
+echo "=== experimental widths 640 / 1152 / 1280 / 1536"
+SCL_EXPERIMENTAL_SHAPES=1 timeout 300 python -m pytest tests/test_gpu_experimental_shapes.py -m gpu -q -p no:cacheprovider > gpurun_out/r2_shapes_tests.log 2>&1
+echo "exit $?"; grep -E "passed|failed" gpurun_out/r2_shapes_tests.log | tail -2
 echo "=== wait-cycle counters (default kernels)"
 timeout 300 python tools/kernel_timing.py > gpurun_out/r2_kernel_timing.txt 2>&1; tail -40 gpurun_out/r2_kernel_timing.txt

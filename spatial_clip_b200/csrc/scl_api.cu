@@ -69,10 +69,21 @@ int resolve_variant(int variant) {
 
 // Output width D: D % 64 == 0 up to 512; 768 and 1024-class widths (D % 256 == 0 up to 1024) run on the CTA-pair
 // kernels only (two D slices in the backward).
+bool experimental_shapes() {
+  // widths whose slice layout (e.g. a 64-column accumulator group) has not been run on a B200 yet
+  static const bool on = [] {
+    const char* e = std::getenv("SCL_EXPERIMENTAL_SHAPES");
+    return e != nullptr && e[0] == '1' && e[1] == 0;
+  }();
+  return on;
+}
 bool shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
   if (m_rows < 1 || n_cols < 1 || d < 64) return false;
   if (d <= 512) return d % 64 == 0;
-  return variant == 1 && d <= 1024 && d % 256 == 0;
+  if (variant != 1) return false;
+  if (d <= 1024 && d % 256 == 0) return true;
+  // 640 / 1152 / 1280 / 1536 (other open_clip widths): same kernels, more D slices
+  return experimental_shapes() && d <= 1536 && d % 64 == 0 && scl::bwd_pair_d_slices(d) > 0;
 }
 // Contraction length of the forward pass: as above, plus the K-concatenated operands of the fp32-accurate mode
 // (3 D, so up to 3072) -- beyond 512 the CTA-pair kernel streams X with Y and any multiple of 64 works.

@@ -474,7 +474,15 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   }
 }
 
-int bwd_pair_d_slices(int d) { return d > 512 ? 2 : 1; }
+// D slices of the backward (TMEM holds dX[64 x <= 512] per SM): the smallest count that cuts D into equal slices of
+// at most 512 columns, each a multiple of 64 (768 -> 2 x 384, 1024 -> 2 x 512, 640 -> 2 x 320, 1152 -> 3 x 384,
+// 1280 -> 4 x 320, 1536 -> 3 x 512); 0 = no such cut
+int bwd_pair_d_slices(int d) {
+  if (d <= 512) return 1;
+  for (int s = 2; s <= 8; ++s)
+    if (d % s == 0 && d / s <= 512 && (d / s) % 64 == 0) return s;
+  return 0;
+}
 
 size_t bwd_pair_smem_bytes(int d, int split) {
   const size_t x_block = (split || d > 512) ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
@@ -504,7 +512,7 @@ static int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles
   return best_c;
 }
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
-  const int pairs = (m_rows + 127) / 128 * (d > 512 ? 2 : 1);
+  const int pairs = (m_rows + 127) / 128 * max(1, bwd_pair_d_slices(d));
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
