@@ -489,28 +489,6 @@ size_t bwd_pair_smem_bytes(int d, int split) {
   return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
 }
 
-// Column chunking for a grid of `units` row blocks (CTAs or CTA pairs) over `slots` concurrently resident
-// units: choose the chunk count that minimises  waves * tiles_per_chunk  (the launch lasts `waves` rounds of
-// the longest chunk), breaking ties towards fewer chunks (each chunk adds a partial-result slab).
-static int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles, int* tiles_per_chunk) {
-  int best_c = 1, best_tpc = n_tiles;
-  double best_cost = 1e30;
-  const int max_c = n_tiles / min_tiles > 1 ? n_tiles / min_tiles : 1;
-  for (int c = 1; c <= max_c; ++c) {
-    const int tpc = (n_tiles + c - 1) / c;
-    const int real_c = (n_tiles + tpc - 1) / tpc;
-    const long long ctas = static_cast<long long>(units) * real_c;
-    const long long waves = (ctas + slots - 1) / slots;
-    const double cost = static_cast<double>(waves) * (tpc + 0.35) + 0.02 * real_c;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best_c = real_c;
-      best_tpc = tpc;
-    }
-  }
-  *tiles_per_chunk = best_tpc;
-  return best_c;
-}
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 127) / 128 * max(1, bwd_pair_d_slices(d));
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;

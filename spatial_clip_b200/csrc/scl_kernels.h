@@ -23,6 +23,28 @@ cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_co
                             float* dx_partial, cudaStream_t stream);
 
 // ---- CTA-pair (cta_group::2) variants
+// Column chunking for a grid of `units` row blocks (CTAs or CTA pairs) over `slots` concurrently resident
+// units: choose the chunk count that minimises  waves * tiles_per_chunk  (the launch lasts `waves` rounds of
+// the longest chunk), breaking ties towards fewer chunks (each chunk adds a partial-result slab).
+inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles, int* tiles_per_chunk) {
+  int best_c = 1, best_tpc = n_tiles;
+  double best_cost = 1e30;
+  const int max_c = n_tiles / min_tiles > 1 ? n_tiles / min_tiles : 1;
+  for (int c = 1; c <= max_c; ++c) {
+    const int tpc = (n_tiles + c - 1) / c;
+    const int real_c = (n_tiles + tpc - 1) / tpc;
+    const long long ctas = static_cast<long long>(units) * real_c;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (tpc + 0.35) + 0.02 * real_c;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best_c = real_c;
+      best_tpc = tpc;
+    }
+  }
+  *tiles_per_chunk = best_tpc;
+  return best_c;
+}
 size_t fwd_pair_smem_bytes(int d);
 int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
 cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
