@@ -30,5 +30,8 @@ timeout 300 python bench.py --steps 5 --warmup 3 --precision fp32 > gpurun_out/r
 echo "=== experimental widths 640 / 1152 / 1280 / 1536"
 SCL_EXPERIMENTAL_SHAPES=1 timeout 300 python -m pytest tests/test_gpu_experimental_shapes.py -m gpu -q -p no:cacheprovider > gpurun_out/r2_shapes_tests.log 2>&1
 echo "exit $?"; grep -E "passed|failed" gpurun_out/r2_shapes_tests.log | tail -2
+echo "=== DSMEM hand-over probe (feasibility of the split-role backward)"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I spatial_clip_b200/csrc tools/dsmem_probe.cu -o /tmp/dsmem_probe 2>/dev/null || cp tools/dsmem_probe.bin /tmp/dsmem_probe
+timeout 60 /tmp/dsmem_probe > gpurun_out/r2_dsmem_probe.txt 2>&1; cat gpurun_out/r2_dsmem_probe.txt
 echo "=== wait-cycle counters (default kernels)"
 timeout 300 python tools/kernel_timing.py > gpurun_out/r2_kernel_timing.txt 2>&1; tail -40 gpurun_out/r2_kernel_timing.txt

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""BASELINE configs[4] sweep on one GPU (or one rank's share of a W-rank job, emulated by B_l = N / W rows against all
-N columns): N in {8192 .. 131072}, D in {512, 768, 1024}, precision bf16 / fp32.  Prints one JSON line per point:
+"""BASELINE configs[4] sweep on one GPU: N in {8192 .. 131072}, D in {512, 768, 1024}, precision bf16 / fp32.
+Prints one JSON line per point:
 ms per fwd+bwd step (CUDA events, median of --iters after --warmup), pairs/s/GPU, algorithmic and executed
 tensor fractions of MEASURED_PEAKS.json.  Needs a B200; developer tool, not part of the bench contract.
 
-    python tools/sweep.py --n 8192 32768 131072 --d 512 1024 --precision bf16 fp32 --world 1 8
+    python tools/sweep.py --n 8192 32768 131072 --d 512 1024 --precision bf16 fp32
 """
 import argparse
 import json
