@@ -10,6 +10,22 @@ for t in 1 2 3; do
       -k "bwd_rows or modules_match or mid_size or full_size or wide" > gpurun_out/r2_tune${t}_tests.log 2>&1
   echo "exit $?"; tail -2 gpurun_out/r2_tune${t}_tests.log
 done
+echo "=== SCL_BWD_MN=1 parity (no transposed copies: MN-major B operand in the gradient GEMM)"
+SCL_BWD_MN=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
+    -k "cta2 and (bwd_rows or modules_match or mid_size or full_size or wide or multi_rank)" > gpurun_out/r2_mn_tests.log 2>&1
+echo "exit $?"; tail -2 gpurun_out/r2_mn_tests.log
+for mn in 0 1; do
+  echo "=== bench SCL_BWD_MN=1 SCL_BWD_TUNE=$((mn * 3))"
+  SCL_BWD_MN=1 SCL_BWD_TUNE=$((mn * 3)) timeout 300 python bench.py --steps 8 --warmup 3 > gpurun_out/r2_bench_mn$mn.json 2> gpurun_out/r2_bench_mn$mn.err
+  python - <<PY
+import json
+try:
+    j = json.load(open("gpurun_out/r2_bench_mn$mn.json")); r = j["roofline"]
+    print("ms/step", round(j["ms_per_step"], 3), "pairs/s", round(j["value"]), "bwd_ms", round(r["launch_ms"], 3), "loss", j["loss"])
+except Exception as e:
+    print("no json", e); print(open("gpurun_out/r2_bench_mn$mn.err").read()[-1500:])
+PY
+done
 for t in 0 1 2 3; do
   echo "=== bench SCL_BWD_TUNE=$t"
   SCL_BWD_TUNE=$t timeout 300 python bench.py --steps 8 --warmup 3 > gpurun_out/r2_bench_tune$t.json 2> gpurun_out/r2_bench_tune$t.err

@@ -7,6 +7,7 @@ raises.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -153,6 +154,9 @@ class CudaOps:
         self.variant = -1  # -1: library default (env SCL_VARIANT), 0: single-CTA kernels, 1: CTA-pair kernels
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
+        # developer knob (read by the library too): the gradient GEMM takes Y itself as an MN-major operand, so no
+        # transposed copies are made or passed (bf16 mode, CTA-pair kernels only; not yet run on a B200)
+        self.mn_major = os.environ.get("SCL_BWD_MN") == "1"
 
     def _cycles(self, name, plan, like):
         """Developer timing mode: a zeroed int64 buffer (16 counters per CTA) when self.cycle_buffers is a dict."""
@@ -398,12 +402,14 @@ class CudaOps:
         if split:
             d //= 3
         n = y_all.shape[0]
+        if y_all_t is None:  # mn_major: the library builds its second tensor map on y_all
+            y_all_t = y_all.new_empty((0, n))
         ws_bytes = self.lib.scl_bwd_workspace_bytes(m, n, d, self.variant)
         if ws_bytes == 0:
             self._check(-2, "scl_bwd_workspace_bytes")
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x_rows.device)
         out = self.empty((m, d), out_dtype, x_rows)
-        a = BwdArgs(_ptr(x_rows), _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], m, n, d, rank, self.variant,
+        a = BwdArgs(_ptr(x_rows), _ptr(y_all), _ptr(y_all_t) or _ptr(y_all), y_all_t.shape[1], m, n, d, rank, self.variant,
                     _ptr(row_stats), _ptr(col_stats), _ptr(pos_col), _ptr(pos_q), _ptr(opp_q_local),
                     _ptr(opp_col_all), _ptr(opp_q_all), pos_col.shape[1], _ptr(gaps), _ptr(scalars), _ptr(grad_out),
                     float(c), float(w), float(mult), col_mode, _ptr(out), _DTYPE_CODE[out_dtype], _ptr(ws), ws_bytes,
@@ -446,6 +452,8 @@ class CudaOps:
         if split:
             d //= 3
         n = y_all.shape[0]
+        if y_all_t is None:  # mn_major
+            y_all_t = y_all.new_empty((0, n))
         plan = self.bwd_plan(m, n, d, split)
         row_coef = self.empty((plan.m_pad, 4), torch.float32, x_rows)
         col_coef = self.empty((plan.n_pad, 4), torch.float32, x_rows)
@@ -461,7 +469,8 @@ class CudaOps:
                                                 pos_col.shape[1], _ptr(row_coef), _ptr(col_coef), st),
                         "scl_bwd_coeffs")
             self._check(self._timed("bwd_rows", x_rows.device, lambda: self.lib.scl_bwd_rows(
-                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t), y_all_t.shape[1], n, d, rank * b_local, _ptr(scalars),
+                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t) or _ptr(y_all), y_all_t.shape[1], n, d, rank * b_local,
+                _ptr(scalars),
                 C.byref(plan),
                 _ptr(row_coef), _ptr(col_coef), _ptr(partial), _ptr(self._cycles("bwd", plan, x_rows)), st)),
                 "scl_bwd_rows")

@@ -282,7 +282,10 @@ int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void*
     if (rc != SCL_OK) return rc;
     rc = make_map(&tm_cols, y_cols, kd, n_cols, kd, 128);
     if (rc != SCL_OK) return rc;
-    rc = make_map(&tm_cols_t, y_cols_t, n_cols, plan->split ? 2 * d : d, ld_t, 128);
+    if (!plan->split && scl::bwd_pair_mn_major())  // SCL_BWD_MN=1: the gradient GEMM reads Y itself (y_cols_t unused)
+      rc = make_map(&tm_cols_t, y_cols, d, n_cols, d, 64);
+    else
+      rc = make_map(&tm_cols_t, y_cols_t, n_cols, plan->split ? 2 * d : d, ld_t, 128);
     if (rc != SCL_OK) return rc;
     return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
                                              plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,

@@ -64,7 +64,9 @@ struct B2Bars {
 // contracted over the K-concatenated rows X' = (h|h|l), Y' = (h|l|h) of width 3 d (x.y ~= xh.yh + xh.yl + xl.yh,
 // the dropped terms are O(2^-18)), G is written as two bf16 tiles G1 + G2 and the gradient GEMM runs three passes
 // G1.Yh + G1.Yl + G2.Yh against the stacked transposed copy [Yh^T ; Yl^T] ([2 d, ld]).  X is always streamed.
-template <int kTune, int kSplit>
+// kMN = 1 (developer knob SCL_BWD_MN, not with kSplit): the gradient GEMM reads Y itself as an MN-major operand
+// (tm_cols_t is then a {64, 64}-box map over the row-major Y [N, D]); no transposed copy of Y exists at all.
+template <int kTune, int kSplit, int kMN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
 bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
                      const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
@@ -190,8 +192,16 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
             for (int b = 0; b < nb; ++b) {
               const int js = (u + b) / ng, g = (u + b) % ng;
               const int n_g = min(256, ds - 256 * g);
-              tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
-                               col0 + js * 64, t_row0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
+              if constexpr (kMN != 0) {
+                // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
+                const int dbase = d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
+                uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
+                tma_load_2d_pair(slot, &tm_cols_t, &bars.full[s], dbase, col0 + js * 64);
+                tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_t, &bars.full[s], dbase + 64, col0 + js * 64);
+              } else {
+                tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
+                                 col0 + js * 64, t_row0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
+              }
             }
           }
         }
@@ -267,13 +277,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
             if (elect_one()) {
               for (int b = 0; b < nb; ++b) {
                 const int js = (u + b) / ng, g = (u + b) % ng;
-                const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g));
+                const uint32_t idesc_acc =
+                    umma_idesc_bf16(128, min(256, ds - 256 * g)) | (kMN != 0 ? kUmmaIdescBMnMajor : 0u);
                 const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(g_tile + js * kB2GSubBytes));
-                const uint64_t b_desc =
-                    umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
+                const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes);
+                // K-major Y^T box: +32 B per K = 16 step; MN-major Y boxes: 16 rows of 128 B = +2048 B per step
+                const uint64_t b_desc = kMN != 0 ? umma_desc_mnmajor_sw128(b_addr, kB2SlotBytes / 2)
+                                                 : umma_desc_kmajor_sw128(b_addr);
+                constexpr int b_step = kMN != 0 ? 128 : 2;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_acc,
+                  tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + b_step * k, idesc_acc,
                                    (lt | p | js | k) != 0 ? 1u : 0u);
               }
               tc_commit_pair(&bars.empty[s]);
@@ -489,13 +503,22 @@ size_t bwd_pair_smem_bytes(int d, int split) {
   return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
 }
 
+// developer knob, read once per process: SCL_BWD_MN=1 -> no transposed copies, MN-major B operand in the gradient GEMM
+bool bwd_pair_mn_major() {
+  static const bool on = [] {
+    const char* e = std::getenv("SCL_BWD_MN");
+    return e != nullptr && e[0] == '1' && e[1] == 0;
+  }();
+  return on;
+}
+
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 127) / 128 * max(1, bwd_pair_d_slices(d));
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 
-template <int kTune, int kSplit>
+template <int kTune, int kSplit, int kMN>
 static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols,
                                           const CUtensorMap& tm_cols_t, int m_rows, int n_cols, int d, int chunks,
                                           int tiles_per_chunk, int m_pad, int diag0, const float* scale_log2,
@@ -507,7 +530,7 @@ static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUte
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune, kSplit>,
+    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune, kSplit, kMN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (err != cudaSuccess) return err;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -516,7 +539,7 @@ static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUte
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);
   dim3 grid(2 * pairs, chunks, d_slices);
-  bwd_rows_pair_kernel<kTune, kSplit><<<grid, kB2Threads, smem, stream>>>(
+  bwd_rows_pair_kernel<kTune, kSplit, kMN><<<grid, kB2Threads, smem, stream>>>(
       tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices, n_tiles, tiles_per_chunk, m_pad, diag0, scale_log2,
       row_coef, col_coef, dx_partial, dbg_t);
   return cudaGetLastError();
@@ -527,22 +550,29 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
                                  float* dx_partial, long long* dbg_t, int split, cudaStream_t stream) {
   if (split)
-    return launch_bwd_rows_pair_t<0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                        diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    return launch_bwd_rows_pair_t<0, 1, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                           diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
   static const int tune = [] {  // developer knob, read once per process
     const char* e = std::getenv("SCL_BWD_TUNE");
     return (e != nullptr && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 0;
   }();
+  if (bwd_pair_mn_major())
+    return tune == 3 ? launch_bwd_rows_pair_t<3, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
+                                                       tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
+                                                       dx_partial, dbg_t, stream)
+                     : launch_bwd_rows_pair_t<0, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
+                                                       tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
+                                                       dx_partial, dbg_t, stream);
   switch (tune) {
-    case 1: return launch_bwd_rows_pair_t<1, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 1: return launch_bwd_rows_pair_t<1, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 2: return launch_bwd_rows_pair_t<2, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 2: return launch_bwd_rows_pair_t<2, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 3: return launch_bwd_rows_pair_t<3, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+    case 3: return launch_bwd_rows_pair_t<3, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
     default: break;
   }
-  return launch_bwd_rows_pair_t<0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
+  return launch_bwd_rows_pair_t<0, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
                                    scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
 }
 

@@ -54,6 +54,7 @@ cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorM
 size_t bwd_pair_smem_bytes(int d, int split);
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
 int bwd_pair_d_slices(int d);
+bool bwd_pair_mn_major();
 cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,

@@ -249,6 +249,22 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Shared-memory matrix descriptor for an MN-major operand tile (the contraction index runs across 128-byte rows):
+// rows of 64 bf16 along M/N, 8 consecutive K rows form a 1024-byte swizzle atom (SBO = 1024 B between atoms along
+// K), further groups of 64 M/N elements sit `lbo_bytes` apart (CUTLASS canonical layout
+// Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).  This is what a TMA SWIZZLE_128B box
+// {64 inner, rows} of a ROW-major [K, MN] matrix looks like, so no transposed copy is needed.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kUmmaIdescBMnMajor = 1u << 16;  // instruction-descriptor bit: B operand is MN-major
+
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulator.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   bit 15 / 16: A / B major (0 = K)   [17,23) N >> 3   [24,29) M >> 4

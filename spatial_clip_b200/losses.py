@@ -126,7 +126,9 @@ class _ContrastiveLossFn(torch.autograd.Function):
         # ---- cap, bf16 copies (gather_features operands, loss.py:21-65).  Single rank + backward wanted: the
         # transposed copies the backward GEMMs need come out of the same pass (dImage needs text^T and vice versa)
         ld_t = (n + 7) // 8 * 8
-        fuse_t = world == 1  # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
+        # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
+        no_t = getattr(ops, "mn_major", False) and not cfg.split  # developer knob: no transposed copies at all
+        fuse_t = world == 1 and not no_t
         # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
         # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
         img_l, txt_l, img_c, txt_c, img_t, txt_t, scalars = ops.prepare(
@@ -168,6 +170,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
             out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
 
         ctx.cfg = cfg
+        ctx.no_t = no_t
         ctx.d = d
         ctx.c = c
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
@@ -209,14 +212,14 @@ class _ContrastiveLossFn(torch.autograd.Function):
         d_img = d_txt = d_scale = None
         img_all_t, txt_all_t = ctx.transposed
         if need_i:
-            if txt_all_t is None:
+            if txt_all_t is None and not ctx.no_t:
                 txt_all_t = ops.transpose_split(txt_all, d, ld_t) if cfg.split else \
                     ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
             d_img = ops.backward_dir(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all,
                                      q_ti_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
                                      ctx.in_dtypes[0], q_ti, split=cfg.split)
         if need_t:
-            if img_all_t is None:
+            if img_all_t is None and not ctx.no_t:
                 img_all_t = ops.transpose_split(img_all, d, ld_t) if cfg.split else \
                     ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
             d_txt = ops.backward_dir(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all,
