@@ -134,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
         "value": pps, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "data": "synthetic", "config": {**workload_config(args.gpus), "precision": args.precision},
         "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
