@@ -76,8 +76,9 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t spins = 0;
+  // every unsuccessful try may have parked for up to hint_ns: keep the watchdog in seconds, not minutes
   while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
-    if (++spins > SCL_SPIN_LIMIT) __trap();
+    if (++spins > (SCL_SPIN_LIMIT >> 7)) __trap();
   }
 }
 
