@@ -106,3 +106,16 @@ def make_spot_batch(
 
 
 LOGIT_SCALES = {"init": 1.0 / 0.07, "capped": 55.0, "max": 100.0}
+
+
+def shuffled_text_ids(tile_ids: torch.Tensor, seed: int, frac: float = 0.125) -> torch.Tensor:
+    """Text-side tile ids that differ from the image-side ones: a seeded ``frac`` of the positions is permuted among
+    itself (the reference API takes the two id vectors separately, losses.py:44-55, and resolves neighbours of image
+    rows in the TEXT id map and vice versa, losses.py:92-108; its own data loader always passes equal vectors)."""
+    g = torch.Generator().manual_seed(seed)
+    n = tile_ids.shape[0]
+    m = max(2, int(round(frac * n)))
+    pos = torch.randperm(n, generator=g)[:m]
+    out = tile_ids.clone()
+    out[pos] = tile_ids[pos.roll(1)]
+    return out

@@ -38,3 +38,19 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def text_ids_for(meta, batch):
+    """Text-side tile ids of a fixture: the image-side ids unless the fixture was minted with different ones."""
+    if "text_ids_seed" in meta:
+        from spatial_clip_b200.synth import shuffled_text_ids
+
+        return shuffled_text_ids(batch.tile_ids, meta["text_ids_seed"])
+    return batch.tile_ids.clone()
+
+
+def unverified_on_gpu(name):
+    """Fixtures added after the last B200 run: excluded from the GPU parametrisations unless SCL_TEST_EXPERIMENTAL=1."""
+    import os
+
+    return "asym" in name and os.environ.get("SCL_TEST_EXPERIMENTAL") != "1"

@@ -38,7 +38,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
-from spatial_clip_b200.synth import make_spot_batch  # noqa: E402
+from spatial_clip_b200.synth import make_spot_batch, shuffled_text_ids  # noqa: E402
 
 REF = Path("/root/reference")
 OUT = Path(__file__).resolve().parent
@@ -81,7 +81,8 @@ def fake_gather(all_img, all_txt, b):
     return gather_features
 
 
-def run_spatial(ref_mod, cls_name, batch, scale, world, ctor, logit_bias=None, capture_labels=False, legacy=False):
+def run_spatial(ref_mod, cls_name, batch, scale, world, ctor, logit_bias=None, capture_labels=False, legacy=False,
+                text_ids=None):
     n = batch.image_features.shape[0]
     b = n // world
     img = batch.image_features.clone().requires_grad_(True)
@@ -115,7 +116,7 @@ def run_spatial(ref_mod, cls_name, batch, scale, world, ctor, logit_bias=None, c
                         batch.neighbor_alphas[sl], s, logit_bias, output_dict=True)
             else:
                 out = m(image_features=img[sl], text_features=txt[sl], logit_scale=s,
-                        image_tile_ids=ids[sl], text_tile_ids=ids[sl],
+                        image_tile_ids=ids[sl], text_tile_ids=(ids if text_ids is None else text_ids)[sl],
                         neighbor_tile_ids=batch.neighbor_tile_ids[sl],
                         neighbor_alphas=batch.neighbor_alphas[sl], logit_bias=logit_bias)
             loss_r = out["contrastive_loss"]
@@ -201,6 +202,19 @@ def main():
         np.savez_compressed(OUT / f"{name}.npz", meta=json.dumps(meta), **res)
         cases[name] = meta
         print(f"{name:38s} loss={res['loss']}")
+
+    if len(sys.argv) > 1 and sys.argv[1] == "--asym-only":
+        # later addition, minted on its own so that the earlier fixtures (zip timestamps) stay byte-identical:
+        # image-side and text-side tile ids differ (world 1: the id all-gather is not exercised)
+        gasym = dict(n=96, d=64, k=8, seed=1008, dup_frac=0.05, self_loops=True)
+        ba = make_spot_batch(**gasym)
+        add("spatial_n96_asym_text_ids", "spatial", gasym, 30.0, 1, SPATIAL_DEFAULT,
+            run_spatial(ref, "SpatialLoss", ba, 30.0, 1, SPATIAL_DEFAULT, capture_labels=True,
+                        text_ids=shuffled_text_ids(ba.tile_ids, 77)), text_ids_seed=77)
+        idx = json.loads((OUT / "index.json").read_text())
+        idx.update(cases)
+        (OUT / "index.json").write_text(json.dumps(idx, indent=1, sort_keys=True))
+        return
 
     g64 = dict(n=64, d=64, k=8, seed=1001)
     # cfg1 smoke shape: N=64, K=8 and K=6, hydra defaults

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, text_ids_for
 from emulated_ops import SplitArithmeticOps
 from spatial_clip_b200 import ClipLoss, SpatialLoss, losses
 from spatial_clip_b200.synth import make_spot_batch
@@ -24,7 +24,7 @@ def test_split_arithmetic_meets_the_fp32_gate(name):
         c = dict(meta["ctor"], precision="fp32")
         if meta["kind"] == "spatial":
             c.pop("cache_labels", None)
-            out = SpatialLoss(**c)(img, txt, s, b.tile_ids, b.tile_ids.clone(), b.neighbor_tile_ids, b.neighbor_alphas)
+            out = SpatialLoss(**c)(img, txt, s, b.tile_ids, text_ids_for(meta, b), b.neighbor_tile_ids, b.neighbor_alphas)
         else:
             out = ClipLoss(**c)(img, txt, s)
         loss = out["contrastive_loss"]

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, text_ids_for
 from spatial_clip_b200.synth import make_spot_batch
 
 pytestmark = [pytest.mark.gpu,
@@ -130,7 +130,7 @@ def _run(meta, **extra):
     c = dict(meta["ctor"], precision="fp32", **extra)
     if meta["kind"] == "spatial":
         c.pop("cache_labels", None)
-        out = SpatialLoss(**c)(img, txt, s, b.tile_ids.cuda(), b.tile_ids.cuda(), b.neighbor_tile_ids.cuda(),
+        out = SpatialLoss(**c)(img, txt, s, b.tile_ids.cuda(), text_ids_for(meta, b).cuda(), b.neighbor_tile_ids.cuda(),
                                b.neighbor_alphas.cuda())
     else:
         out = ClipLoss(**c)(img, txt, s)

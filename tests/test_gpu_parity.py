@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, text_ids_for, unverified_on_gpu
 from oracle.contrastive_oracle import (clip_loss_oracle, dense_labels, soft_label_triples,
                                        spatial_loss_oracle)
 from spatial_clip_b200.synth import make_spot_batch
@@ -75,15 +75,17 @@ def test_row_statistics(ops, m, n, d, s):
 
 
 # ---------------------------------------------------------------- layer 3: integer path, bit exact
-@pytest.mark.parametrize("name", [n for n in golden_names("spatial", world=1) if "bias" not in n and "legacy" not in n])
+@pytest.mark.parametrize("name", [n for n in golden_names("spatial", world=1)
+                                  if "bias" not in n and "legacy" not in n and not unverified_on_gpu(n)])
 def test_positive_lists_bit_exact_vs_reference_labels(ops, name):
     meta, gold = load_golden(name)
     if "labels_i_t" not in gold:
         pytest.skip("no dense labels stored")
     b = make_spot_batch(**meta["gen"])
     n, k = b.neighbor_tile_ids.shape
-    col, w, q = ops.build_positives(b.tile_ids.cuda(), b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda(), n, k,
-                                    meta["ctor"].get("neighbor_alpha_scale", 1.0), 0, b.image_features.cuda())
+    # image rows resolve their neighbours in the TEXT id map (losses.py:92,102-108)
+    col, w, q = ops.build_positives(text_ids_for(meta, b).cuda(), b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda(),
+                                    n, k, meta["ctor"].get("neighbor_alpha_scale", 1.0), 0, b.image_features.cuda())
     torch.cuda.synchronize()
     col, w, q = col.cpu().numpy(), w.cpu().numpy(), q.cpu().numpy()
     dense = np.zeros((n, n), dtype=np.float32)
@@ -168,7 +170,7 @@ def _module_run(meta, dtype=torch.float32):
     c = dict(meta["ctor"])
     if meta["kind"] == "spatial":
         mod = SpatialLoss(**c)
-        out = mod(img, txt, s, b.tile_ids.cuda(), b.tile_ids.cuda(), b.neighbor_tile_ids.cuda(),
+        out = mod(img, txt, s, b.tile_ids.cuda(), text_ids_for(meta, b).cuda(), b.neighbor_tile_ids.cuda(),
                   b.neighbor_alphas.cuda())
     else:
         mod = ClipLoss(**c)
@@ -184,14 +186,14 @@ def _oracle_on_bf16_inputs(meta, b):
     txt = b.text_features.to(torch.bfloat16).float().numpy()
     c = meta["ctor"]
     if meta["kind"] == "spatial":
-        return spatial_loss_oracle(img, txt, meta["scale"], b.tile_ids.numpy(), b.tile_ids.numpy(),
+        return spatial_loss_oracle(img, txt, meta["scale"], b.tile_ids.numpy(), text_ids_for(meta, b).numpy(),
                                    b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy(), 1,
                                    c.get("cap_logit_scale"), c.get("temp_reg_weight", 0.0),
                                    c.get("neighbor_alpha_scale", 1.0))
     return clip_loss_oracle(img, txt, meta["scale"])
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names(world=1) if "legacy" not in n])
+@pytest.mark.parametrize("name", [n for n in golden_names(world=1) if "legacy" not in n and not unverified_on_gpu(n)])
 def test_modules_match_reference(ops, name):
     """Gate (SURVEY 8d "parity gates", bf16 mode): against the oracle evaluated in fp64 on the SAME bf16-rounded
     inputs -- loss rel 2e-5 (+ the fp32-LSE floor), d_scale rel 1e-3, grads 1.2e-2 of ||grad||_inf (dL/dz is

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, text_ids_for
 from emulated_ops import EmulatedOps
 from spatial_clip_b200 import ClipLoss, GlobalMappingMultiPositiveClipLoss, SpatialLoss, losses
 from spatial_clip_b200.synth import make_spot_batch
@@ -40,7 +40,7 @@ def _run_rank(meta, rank, world, mod):
     bias = torch.tensor(meta["logit_bias"]) if "logit_bias" in meta else None
     if meta["kind"] == "spatial":
         out = mod(image_features=img, text_features=txt, logit_scale=s, image_tile_ids=b.tile_ids,
-                  text_tile_ids=b.tile_ids.clone(), neighbor_tile_ids=b.neighbor_tile_ids,
+                  text_tile_ids=text_ids_for(meta, b), neighbor_tile_ids=b.neighbor_tile_ids,
                   neighbor_alphas=b.neighbor_alphas, logit_bias=bias)
     else:
         out = mod(image_features=img, text_features=txt, logit_scale=s, logit_bias=bias)

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, text_ids_for
 from oracle.contrastive_oracle import (clip_loss_oracle, dense_labels, soft_label_triples,
                                        spatial_loss_oracle)
 from spatial_clip_b200.synth import make_spot_batch
@@ -15,12 +15,16 @@ def _inputs(meta):
             b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy())
 
 
+def _text_ids(meta):
+    return text_ids_for(meta, make_spot_batch(**meta["gen"])).numpy()
+
+
 @pytest.mark.parametrize("name", golden_names("spatial"))
 def test_spatial_oracle_matches_reference(name):
     meta, gold = load_golden(name)
     img, txt, ids, nbr, alpha = _inputs(meta)
     c = meta["ctor"]
-    res = spatial_loss_oracle(img, txt, meta["scale"], ids, ids, nbr, alpha, world_size=meta["world"],
+    res = spatial_loss_oracle(img, txt, meta["scale"], ids, _text_ids(meta), nbr, alpha, world_size=meta["world"],
                               cap_logit_scale=c.get("cap_logit_scale"), temp_reg_weight=c.get("temp_reg_weight", 0.0),
                               neighbor_alpha_scale=c.get("neighbor_alpha_scale", 1.0),
                               local_loss=c["local_loss"], gather_with_grad=c["gather_with_grad"])
@@ -41,12 +45,14 @@ def test_soft_label_triples_bit_exact(name):
     if "labels_i_t" not in gold:
         pytest.skip("no dense labels stored")
     _, _, ids, nbr, alpha = _inputs(meta)
-    rows, _ = soft_label_triples(ids, nbr, alpha, meta["ctor"].get("neighbor_alpha_scale", 1.0), rank=0)
-    dense = dense_labels(rows, len(ids))
-    # the reference's labels BEFORE F.normalize(p=1): bit-exact fp32 equality
-    assert dense.dtype == np.float32
-    assert np.array_equal(dense.view(np.uint32), gold["labels_i_t"].view(np.uint32))
-    assert np.array_equal(dense.view(np.uint32), gold["labels_t_i"].view(np.uint32))
+    scale = meta["ctor"].get("neighbor_alpha_scale", 1.0)
+    # the reference's labels BEFORE F.normalize(p=1): bit-exact fp32 equality.  Image rows resolve their neighbours in
+    # the TEXT id map, text rows in the IMAGE id map (losses.py:92-93,102-108)
+    for id_map, key in ((_text_ids(meta), "labels_i_t"), (ids, "labels_t_i")):
+        rows, _ = soft_label_triples(id_map, nbr, alpha, scale, rank=0)
+        dense = dense_labels(rows, len(ids))
+        assert dense.dtype == np.float32
+        assert np.array_equal(dense.view(np.uint32), gold[key].view(np.uint32)), key
 
 
 def test_label_invariants_from_reference_notebook():
