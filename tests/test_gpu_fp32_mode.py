@@ -172,3 +172,69 @@ def test_fp32_mode_mid_size_vs_dense_checker(ops):
     assert abs(float(loss) - float(want_loss)) <= 1e-5 * float(want_loss) + 2e-6
     for got, ref in ((img.grad, wi), (txt.grad, wt)):
         assert (got.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def _rank_worker(rank, world, port, name, q):
+    import traceback
+
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        os.environ["SCL_VARIANT"] = "1"
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from spatial_clip_b200 import SpatialLoss
+
+        torch.cuda.set_device(0)
+        meta, _ = load_golden(name)
+        b = make_spot_batch(**meta["gen"]).rank_slice(rank, world)
+        img = b.image_features.cuda().requires_grad_(True)
+        txt = b.text_features.cuda().requires_grad_(True)
+        s = torch.tensor(float(meta["scale"]), device="cuda", requires_grad=True)
+        out = SpatialLoss(**meta["ctor"], precision="fp32")(img, txt, s, b.tile_ids.cuda(), b.tile_ids.cuda(),
+                                                             b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())
+        out["contrastive_loss"].backward()
+        torch.cuda.synchronize()
+        q.put((rank, float(out["contrastive_loss"].detach()), img.grad.cpu().numpy(), txt.grad.cpu().numpy(),
+               float(s.grad)))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("name", ["spatial_n256_w2", "spatial_n256_w4_ll0_gwg0"])
+def test_fp32_mode_multi_rank_on_one_gpu(ops, name):
+    """The (h|l|h) column operands travel through the all-gather; statistics exchange as in the bf16 mode."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    meta, gold = load_golden(name)
+    world = meta["world"]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, name, q), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = []
+    try:
+        for _ in range(world):
+            item = q.get(timeout=150)
+            assert len(item) == 5, f"rank {item[0]} raised:\n{item[1]}"
+            got.append(item)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
+    bl = meta["gen"]["n"] // world
+    for rank, loss, gi, gt, ds in got:
+        sl = slice(rank * bl, (rank + 1) * bl)
+        assert abs(loss - gold["loss"][rank]) <= 1e-5 * abs(gold["loss"][rank]) + 2e-6 + 2e-7 * meta["scale"]
+        assert abs(ds - gold["d_scale"][rank]) <= 3e-4 * abs(gold["d_scale"][rank]) + 2e-6
+        floor = 3e-6 * meta["scale"] * 0.5 / bl
+        for got_g, ref in ((gi, gold["d_image"][sl]), (gt, gold["d_text"][sl])):
+            assert np.abs(got_g - ref).max() <= 1e-4 * np.abs(ref).max() + floor
