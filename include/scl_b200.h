@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SCL_ABI_VERSION 4
+#define SCL_ABI_VERSION 5
 #define SCL_OK 0
 #define SCL_ERR_INVALID_ARG (-1)
 #define SCL_ERR_UNSUPPORTED_SHAPE (-2)
@@ -103,6 +103,17 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
                      const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, long long* dbg_cycles,
                      void* stream);
 
+/* ---- the same pass + in-pass retrieval ranks (CTA-pair kernels only) ------------------------
+ * ranks[i] = number of columns j in the LOCAL block [first_col, first_col + m_rows), j != first_col + i, whose
+ * similarity with row i exceeds that of the row's own pair: the position of the matching profile in the in-batch
+ * image -> gene retrieval.  Replaces the [B_l, B_l] logits matmul + topk the LightningModule runs every step only to
+ * find that position (/root/reference/src/models/spatial_clip_module.py:68,106,113,127;
+ * src/models/components/metrics.py:22-36): Recall@k = mean(ranks < k).  diag_z (float[m_rows]) and rank_partial
+ * (int32[plan.n_slots * plan.m_pad]) are work areas. */
+int scl_fwd_rowstats_ranks(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
+                           const scl_plan* plan, void* partial, int first_col, float* diag_z, int32_t* rank_partial,
+                           int32_t* ranks, void* stream);
+
 /* merge partials and add the positive logits: row_stats[i] = {LSE_i/ln2, E_p[z], Var_p[z], sum_k q_k z_ik} */
 int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int d, const void* x_rows,
                      const void* y_all, const int32_t* pos_col, const float* pos_q, int k_plus_1, void* row_stats,
@@ -164,6 +175,8 @@ typedef struct scl_fwd_args {
   void* stats_i; void* stats_t;                            /* float4[b_local]                               */
   float* sums6; float* out4;
   void* workspace; size_t workspace_bytes;                 /* >= scl_fwd_workspace_bytes(...)               */
+  int32_t* ranks_out;                                      /* NULL, or int32[b_local]: image -> gene retrieval ranks
+                                                              in the local block (scl_fwd_rowstats_ranks)      */
 } scl_fwd_args;
 size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant);
 int scl_fwd_all(const scl_fwd_args* a, void* stream);

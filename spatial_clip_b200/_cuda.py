@@ -41,7 +41,7 @@ class FwdArgs(C.Structure):
                 ("txt_ids_all", _VP), ("nbr_ids", _VP), ("nbr_alpha", _VP), ("k", _I), ("alpha_scale", _F),
                 ("same_ids", _I), ("c", _F), ("w", _F), ("finalize_scalars", _I), ("col_it", _VP), ("w_it", _VP),
                 ("q_it", _VP), ("col_ti", _VP), ("w_ti", _VP), ("q_ti", _VP), ("stats_i", _VP), ("stats_t", _VP),
-                ("sums6", _VP), ("out4", _VP), ("workspace", _VP), ("workspace_bytes", _SZ)]
+                ("sums6", _VP), ("out4", _VP), ("workspace", _VP), ("workspace_bytes", _SZ), ("ranks_out", _VP)]
 
 
 class BwdArgs(C.Structure):
@@ -72,6 +72,9 @@ EXPORTS = {
                                       C.c_void_p]),
     "scl_fwd_rowstats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "scl_fwd_rowstats_ranks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.POINTER(SclPlan), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "scl_row_finalize": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "scl_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -112,7 +115,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 4:
+    if lib.scl_abi_version() != 5:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -356,9 +359,10 @@ class CudaOps:
         return img, txt, img, txt, img_t, txt_t, scal
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars):
+                    finalize_scalars, want_ranks=False):
         """Soft targets + both fused similarity/LSE passes + reductions: scl_fwd_all.
-        ids = None (plain CLIP) or (img_ids_all, txt_ids_all, nbr_ids, nbr_alpha, same_ids)."""
+        ids = None (plain CLIP) or (img_ids_all, txt_ids_all, nbr_ids, nbr_alpha, same_ids).
+        want_ranks: also count, in the image-rows pass, each row's in-batch retrieval rank (self.last_ranks)."""
         st = self._stream(img_l)
         n, d = img_all.shape
         kp1 = k + 1
@@ -382,11 +386,17 @@ class CudaOps:
                     _ptr(scalars), _ptr(ids[0]) if ids else None, _ptr(ids[1]) if ids else None,
                     _ptr(ids[2]) if ids else None, _ptr(ids[3]) if ids else None, k, float(alpha_scale), int(same),
                     float(c), float(w), int(finalize_scalars), _ptr(col_it), _ptr(w_it), _ptr(q_it), _ptr(col_ti),
-                    _ptr(w_ti), _ptr(q_ti), _ptr(stats_i), _ptr(stats_t), _ptr(sums6), _ptr(out4), _ptr(ws), ws_bytes)
+                    _ptr(w_ti), _ptr(q_ti), _ptr(stats_i), _ptr(stats_t), _ptr(sums6), _ptr(out4), _ptr(ws), ws_bytes,
+                    None)
+        ranks = None
+        if want_ranks:
+            ranks = torch.empty((b_local,), dtype=torch.int32, device=dev)
+            a.ranks_out = _ptr(ranks)
         with _DeviceGuard(dev):
             self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
-        self.launches += (3 if k > 0 else 1) * (1 if same else 2) + 5 + (1 if finalize_scalars else 0)
-        return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4
+        self.launches += (3 if k > 0 else 1) * (1 if same else 2) + 5 + (1 if finalize_scalars else 0) + \
+            (2 if want_ranks else 0)
+        return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks
 
     def backward_dir(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                      b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local, split=False):

@@ -226,6 +226,29 @@ int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_c
                                           static_cast<cudaStream_t>(stream)));
 }
 
+int scl_fwd_rowstats_ranks(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
+                           const scl_plan* plan, void* partial, int first_col, float* diag_z, int32_t* rank_partial,
+                           int32_t* ranks, void* stream) {
+  if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr ||
+      diag_z == nullptr || rank_partial == nullptr || ranks == nullptr || first_col < 0 || first_col + m_rows > n_cols)
+    return SCL_ERR_INVALID_ARG;
+  if (plan->variant != 1 || !fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = cuda_rc(scl::launch_retrieval_diag(x_rows, m_rows, y_cols, d, first_col, diag_z, st));
+  if (rc != SCL_OK) return rc;
+  CUtensorMap tm_rows, tm_cols;
+  rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
+  if (rc != SCL_OK) return rc;
+  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
+  if (rc != SCL_OK) return rc;
+  rc = cuda_rc(scl::launch_fwd_rowstats_pair_ranks(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks,
+                                                   plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
+                                                   static_cast<float4*>(partial), diag_z, first_col, first_col + m_rows,
+                                                   rank_partial, st));
+  if (rc != SCL_OK) return rc;
+  return cuda_rc(scl::launch_retrieval_rank_sum(rank_partial, plan->n_slots, plan->m_pad, m_rows, ranks, st));
+}
+
 int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int d, const void* x_rows,
                      const void* y_all, const int32_t* pos_col, const float* pos_q, int k_plus_1, void* row_stats,
                      void* stream) {
@@ -342,7 +365,9 @@ size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int vari
   if (scl_fwd_plan(b_local, n_global, d, variant, &p) != SCL_OK) return 0;
   const size_t partial = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
   const size_t hash = k > 0 ? align256(scl::positives_hash_bytes(n_global)) : 0;
-  return 2 * partial + hash;
+  // + the retrieval-rank work areas (rank partials, own-pair similarities); small, so always included
+  const size_t ranks = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 4) + align256(static_cast<size_t>(p.m_pad) * 4);
+  return 2 * partial + hash + ranks;
 }
 
 int scl_fwd_all(const scl_fwd_args* a, void* stream) {
@@ -358,6 +383,9 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   void* part_t = ws + partial_bytes;
   void* hash = ws + 2 * partial_bytes;
   const size_t hash_bytes = a->k > 0 ? scl::positives_hash_bytes(a->n_global) : 0;
+  char* rank_ws = ws + 2 * partial_bytes + (a->k > 0 ? align256(hash_bytes) : 0);
+  int32_t* rank_partial = reinterpret_cast<int32_t*>(rank_ws);
+  float* diag_z = reinterpret_cast<float*>(rank_ws + align256(static_cast<size_t>(p.n_slots) * p.m_pad * 4));
   // soft targets: image rows use the text-id map, text rows the image-id map (losses.py:102-108)
   rc = scl_build_positives(a->txt_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
                            a->rank, a->k > 0 ? hash : nullptr, hash_bytes, a->col_it, a->w_it, a->q_it, stream);
@@ -367,8 +395,12 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
                              a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti, stream);
     if (rc != SCL_OK) return rc;
   }
-  rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
-                        nullptr, stream);
+  if (a->ranks_out != nullptr)  // image -> gene retrieval ranks within the local block, counted in the same pass
+    rc = scl_fwd_rowstats_ranks(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i,
+                                a->rank * a->b_local, diag_z, rank_partial, a->ranks_out, stream);
+  else
+    rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
+                          nullptr, stream);
   if (rc != SCL_OK) return rc;
   rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1, a->stats_i,
                         stream);

@@ -44,12 +44,18 @@ struct F2Bars {
   uint32_t tmem_base;
 };
 
+// kRank = 1 (in-pass retrieval ranks): every row additionally counts the columns of the LOCAL block
+// [loc_lo, loc_hi) whose similarity exceeds the row's own pair diag_z[row] (own column loc_lo + row excluded), i.e.
+// the position of the matching gene profile in the image -> gene retrieval that the reference finds with a
+// [B_l, B_l] matmul + topk (spatial_clip_module.py:68, metrics.py:22-36).  rank_part mirrors `partial`'s slots.
+template <int kRank>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
 fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, D], box {64, 128}
                          const __grid_constant__ CUtensorMap tm_cols,  // Y [N, D], box {64, 128}
                          int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad,
                          const float* __restrict__ scale_log2_ptr, float4* __restrict__ partial,
-                         float* __restrict__ dbg_z, int dbg_ld, long long* __restrict__ dbg_t) {
+                         float* __restrict__ dbg_z, int dbg_ld, long long* __restrict__ dbg_t,
+                         const float* __restrict__ diag_z, int loc_lo, int loc_hi, int* __restrict__ rank_part) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ F2Bars bars;
   const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
@@ -171,6 +177,9 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     const float s2 = __ldg(scale_log2_ptr);
     float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
     long long w_tf = 0;
+    int above = 0;  // kRank: local columns scoring above this row's own pair
+    float zd = 0.f;
+    if constexpr (kRank != 0) zd = row < m_rows ? __ldg(diag_z + row) : INFINITY;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       mbar_wait_warp(&bars.tmem_full[buf], (lt >> 1) & 1, timed, w_tf);
@@ -244,6 +253,16 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
             s_ezz = fmaf(t, x, s_ezz);
           }
         }
+        if constexpr (kRank != 0) {
+          if (col0 < loc_hi && col0 + 32 > loc_lo) {  // warp-uniform: this chunk touches the local block
+            const int own = loc_lo + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cidx = col0 + j;
+              above += (cidx >= loc_lo && cidx < loc_hi && cidx != own && __uint_as_float(r[j]) > zd) ? 1 : 0;
+            }
+          }
+        }
         if (dbg_z != nullptr && row < m_rows) {
           const int n_valid = min(32, n_cols - col0);
 #pragma unroll
@@ -265,6 +284,7 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     }
     const int slot = blockIdx.y * 4 + hh;
     partial[static_cast<size_t>(slot) * m_pad + row] = make_float4(m, s_e, s_ez, s_ezz);
+    if constexpr (kRank != 0) rank_part[static_cast<size_t>(slot) * m_pad + row] = above;
   }
 
   tc_fence_before();
@@ -286,27 +306,47 @@ int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chu
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 
-cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
-                                     int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
-                                     float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
-                                     cudaStream_t stream) {
+template <int kRank>
+static cudaError_t launch_fwd_rowstats_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
+                                              int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                                              const float* scale_log2, float4* partial, float* dbg_z, int dbg_ld,
+                                              long long* dbg_t, const float* diag_z, int loc_lo, int loc_hi,
+                                              int* rank_part, cudaStream_t stream) {
   const size_t smem = fwd_pair_smem_bytes(d);
   // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(fwd_rowstats_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    cudaError_t err =
+        cudaFuncSetAttribute(fwd_rowstats_pair_kernel<kRank>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (err != cudaSuccess) return err;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
   dim3 grid(2 * pairs, chunks);
-  fwd_rowstats_pair_kernel<<<grid, kF2Threads, smem, stream>>>(tm_rows, tm_cols, m_rows, n_cols, d, n_tiles,
-                                                               tiles_per_chunk, m_pad, scale_log2, partial, dbg_z,
-                                                               dbg_ld, dbg_t);
+  fwd_rowstats_pair_kernel<kRank><<<grid, kF2Threads, smem, stream>>>(tm_rows, tm_cols, m_rows, n_cols, d, n_tiles,
+                                                                      tiles_per_chunk, m_pad, scale_log2, partial,
+                                                                      dbg_z, dbg_ld, dbg_t, diag_z, loc_lo, loc_hi,
+                                                                      rank_part);
   return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
+                                     int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
+                                     float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
+                                     cudaStream_t stream) {
+  return launch_fwd_rowstats_pair_t<0>(tm_rows, tm_cols, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, scale_log2,
+                                       partial, dbg_z, dbg_ld, dbg_t, nullptr, 0, 0, nullptr, stream);
+}
+
+cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
+                                           int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                                           const float* scale_log2, float4* partial, const float* diag_z, int loc_lo,
+                                           int loc_hi, int* rank_part, cudaStream_t stream) {
+  return launch_fwd_rowstats_pair_t<1>(tm_rows, tm_cols, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, scale_log2,
+                                       partial, nullptr, 0, nullptr, diag_z, loc_lo, loc_hi, rank_part, stream);
 }
 
 }  // namespace scl

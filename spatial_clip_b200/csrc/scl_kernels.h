@@ -51,6 +51,10 @@ cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorM
                                      int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
                                      float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
                                      cudaStream_t stream);
+cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
+                                           int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
+                                           const float* scale_log2, float4* partial, const float* diag_z, int loc_lo,
+                                           int loc_hi, int* rank_part, cudaStream_t stream);
 size_t bwd_pair_smem_bytes(int d, int split);
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
 int bwd_pair_d_slices(int d);
@@ -91,6 +95,12 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
 cudaError_t launch_split_cast(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d,
                               cudaStream_t stream);
 cudaError_t launch_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, cudaStream_t stream);
+
+// ---- in-pass retrieval ranks (scl_rank.cu)
+cudaError_t launch_retrieval_diag(const void* x_rows, int m_rows, const void* y_cols, int d, int first_col,
+                                  float* diag_z, cudaStream_t stream);
+cudaError_t launch_retrieval_rank_sum(const int* rank_part, int n_slots, int m_pad, int m_rows, int* ranks,
+                                      cudaStream_t stream);
 
 cudaError_t launch_unpack_records(const float* in, int world, int rec_floats, int n_comp, float* const* outs,
                                   const int* offs, const int* lens, cudaStream_t stream);

@@ -94,6 +94,7 @@ class _Cfg:
     alpha_scale: float
     group: object = None
     split: bool = False  # fp32-accurate mode: operands carried as bf16 hi/lo pairs
+    want_ranks: bool = False  # also count every local image row's in-batch retrieval rank
 
 
 def _col_mode(cfg: _Cfg) -> int:
@@ -161,9 +162,11 @@ class _ContrastiveLossFn(torch.autograd.Function):
         # 113-121), row reductions and the loss scalars: one host call
         global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
         c = 0.5 / (n if global_clip else b_local)
-        (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4 = ops.forward_all(
+        (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
             img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
-            finalize_scalars=not global_clip)
+            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks)
+        if ranks is None:
+            ranks = torch.empty((0,), dtype=torch.int32, device=dev)
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
             # all-gather + fixed-order sum (bitwise identical on every rank, unlike an all-reduce tree)
             sums6 = _all_gather_rows(sums6.reshape(1, 6), world, cfg.group).sum(dim=0)
@@ -178,8 +181,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ctx.transposed = (img_t, txt_t)  # None unless produced above
         ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
                               q_ti)
-        ctx.mark_non_differentiable(col_it, w_it, q_it)
-        return out4[0].clone(), col_it, w_it, q_it
+        ctx.mark_non_differentiable(col_it, w_it, q_it, ranks)
+        return out4[0].clone(), col_it, w_it, q_it, ranks
 
     @staticmethod
     def backward(ctx, grad_loss, *_unused):
@@ -235,7 +238,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
 # modules
 # ------------------------------------------------------------------------------------------------
 class _LossBase(nn.Module):
-    def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod, precision="bf16"):
+    def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod, precision="bf16",
+                 track_retrieval_ranks=False):
         super().__init__()
         if use_horovod:
             raise NotImplementedError("horovod exchange is out of scope; use torch.distributed (NCCL)")
@@ -245,6 +249,12 @@ class _LossBase(nn.Module):
         # "fp32": operands carried as bf16 hi/lo pairs, three tensor-core products per GEMM, dL/dz as two bf16 tiles
         #         (loss rel 1e-5, grads 1e-4 of max vs the fp32 reference; ~3x the tensor work; CTA-pair kernels)
         self.precision = precision
+        # In-pass retrieval metrics: after each forward, ``last_retrieval_ranks`` holds, per local image
+        # row, how many gene profiles of the local batch score above the matching one -- the quantity the reference's
+        # LightningModule recovers with a [B_l, B_l] logits matmul + topk (spatial_clip_module.py:68,
+        # metrics.py:22-36); Recall@k = (ranks < k).float().mean(), see spatial_clip_b200/metrics.py
+        self.track_retrieval_ranks = bool(track_retrieval_ranks)
+        self.last_retrieval_ranks = None
         self.local_loss = bool(local_loss)
         self.gather_with_grad = bool(gather_with_grad)
         self.use_horovod = False
@@ -286,8 +296,9 @@ class SpatialLoss(_LossBase):
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, rank: Optional[int] = None,
                  world_size: Optional[int] = None, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
-                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16"):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision)
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16",
+                 track_retrieval_ranks: bool = False):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks)
         self.cap_logit_scale = cap_logit_scale
         self.temp_reg_weight = float(temp_reg_weight or 0.0)
         self.float32_logits = float32_logits  # logits are always fp32 on chip
@@ -306,11 +317,13 @@ class SpatialLoss(_LossBase):
             raise ValueError("tile ids must be [B] and neighbour ids / alphas [B, K]")
         cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
                    self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
-                   self.precision == "fp32")
-        loss, col, w, q = _ContrastiveLossFn.apply(image_features, text_features,
-                                                   self._scale_tensor(logit_scale, image_features), image_tile_ids,
-                                                   text_tile_ids, neighbor_tile_ids, neighbor_alphas, cfg)
+                   self.precision == "fp32", self.track_retrieval_ranks)
+        loss, col, w, q, ranks = _ContrastiveLossFn.apply(image_features, text_features,
+                                                          self._scale_tensor(logit_scale, image_features),
+                                                          image_tile_ids, text_tile_ids, neighbor_tile_ids,
+                                                          neighbor_alphas, cfg)
         self.last_positives = (col, w, q)
+        self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
         return {"contrastive_loss": loss}
 
 
@@ -319,18 +332,19 @@ class ClipLoss(_LossBase):
 
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
                  rank: Optional[int] = None, world_size: Optional[int] = None, use_horovod: bool = False,
-                 precision: str = "bf16"):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision)
+                 precision: str = "bf16", track_retrieval_ranks: bool = False):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks)
         self.cache_labels = cache_labels  # labels are implicit (the diagonal); nothing to cache
 
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
                 logit_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self._check_features(image_features, text_features, logit_bias)
         cfg = _Cfg("clip", self.rank, self.world_size, self.local_loss, self.gather_with_grad, None, 0.0, 1.0,
-                   self.process_group, self.precision == "fp32")
-        loss, _, _, _ = _ContrastiveLossFn.apply(image_features, text_features,
-                                                 self._scale_tensor(logit_scale, image_features), None, None, None,
-                                                 None, cfg)
+                   self.process_group, self.precision == "fp32", self.track_retrieval_ranks)
+        loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,
+                                                        self._scale_tensor(logit_scale, image_features), None, None,
+                                                        None, None, cfg)
+        self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
         return {"contrastive_loss": loss}
 
 
@@ -340,9 +354,10 @@ class GlobalMappingMultiPositiveClipLoss(SpatialLoss):
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
                  rank: Optional[int] = 0, world_size: Optional[int] = 1, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
-                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16"):
+                 float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16",
+                 track_retrieval_ranks: bool = False):
         super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, cap_logit_scale,
-                         temp_reg_weight, float32_logits, neighbor_alpha_scale, precision)
+                         temp_reg_weight, float32_logits, neighbor_alpha_scale, precision, track_retrieval_ranks)
         self.cache_labels = cache_labels
 
     def forward(self, image_features, text_features, image_tile_ids, text_tile_ids, neighbor_tile_ids,

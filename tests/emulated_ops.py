@@ -120,7 +120,7 @@ class EmulatedOps:
         return y_t
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars):
+                    finalize_scalars, want_ranks=False):
         if ids is None:
             it = ti = self.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
         else:
@@ -133,7 +133,14 @@ class EmulatedOps:
         stats_t = self.row_finalize(part_t, plan_t, txt_l, img_all, ti[0], ti[2])
         sums6 = self.reduce_rows(stats_i, stats_t, scalars)
         out4 = self.loss_scalars(sums6, scalars, c, w) if finalize_scalars else None
-        return it, ti, stats_i, stats_t, sums6, out4
+        ranks = None
+        if want_ranks:  # contract of scl_fwd_rowstats_ranks: local columns scoring above the row's own pair
+            lo = rank * b_local
+            z = img_l.double() @ txt_all[lo:lo + b_local].double().t()
+            above = z > z.diagonal()[:, None]
+            above.fill_diagonal_(False)
+            ranks = above.sum(1).to(torch.int32)
+        return it, ti, stats_i, stats_t, sums6, out4, ranks
 
     def backward_dir(self, *args, split=False):
         return self.bwd_rows(*args[:-1], opp_q_local=args[-1])

@@ -219,3 +219,42 @@ def test_gloo_moves_bf16_payloads():
         sl = slice(rank * 128, (rank + 1) * 128)
         assert abs(loss - gold["loss"][rank]) <= 1e-3 * abs(gold["loss"][rank])
         assert np.abs(gi - gold["d_image"][sl]).max() <= 3e-2 * np.abs(gold["d_image"][sl]).max()
+
+
+# ---------------------------------------------------------------- in-pass retrieval ranks
+def _reference_recall_at_k(logits, k):
+    """RecallAtK.update of /root/reference/src/models/components/metrics.py:22-36, restated."""
+    k_eff = min(k, logits.size(1))
+    _, top = torch.topk(logits, k_eff, dim=1)
+    target = torch.arange(logits.size(0))
+    return torch.any(top == target.view(-1, 1), dim=1).float().mean().item()
+
+
+@pytest.mark.parametrize("n,k_nbr", [(64, 8), (5, 8), (300, 0)])
+def test_retrieval_ranks_reproduce_reference_recall(n, k_nbr, emulated):
+    from spatial_clip_b200.metrics import RecallAtKFromRanks, recall_at_k
+
+    b = make_spot_batch(n=n, d=64, k=k_nbr, seed=31 + n)
+    # harder than the generator's default (positives at cos 0.6) so that R@1 is not trivially 1
+    noise = torch.nn.functional.normalize(torch.randn(n, 64, generator=torch.Generator().manual_seed(n)), dim=-1)
+    txt = torch.nn.functional.normalize(0.3 * b.image_features + noise, dim=-1)
+    if k_nbr:
+        mod = SpatialLoss(track_retrieval_ranks=True, temp_reg_weight=0.05)
+        mod(b.image_features, txt, torch.tensor(20.0), b.tile_ids, b.tile_ids, b.neighbor_tile_ids, b.neighbor_alphas)
+    else:
+        mod = ClipLoss(track_retrieval_ranks=True)
+        mod(b.image_features, txt, torch.tensor(20.0))
+    ranks = mod.last_retrieval_ranks
+    assert ranks.dtype == torch.int32 and ranks.shape == (n,)
+    logits = b.image_features @ txt.t() * 20.0  # what spatial_clip_module.py:68 materialises
+    acc = RecallAtKFromRanks()
+    acc.update(ranks)
+    for k in (1, 5, 10):
+        want = _reference_recall_at_k(logits, k)
+        assert abs(recall_at_k(ranks, k).item() - want) < 1e-6
+        assert abs(acc.compute()[f"R@{k}"] - want) < 1e-6
+    assert 0.0 < recall_at_k(ranks, 1).item() < 1.0 or n <= 5
+    # off by default: nothing extra is computed or kept
+    plain = ClipLoss()
+    plain(b.image_features, txt, torch.tensor(20.0))
+    assert plain.last_retrieval_ranks is None
