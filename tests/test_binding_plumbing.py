@@ -135,3 +135,62 @@ def test_unsupported_width_is_refused_before_any_launch(plumbing):
     with pytest.raises(_cuda.SclError) as ei:
         ClipLoss()(b.image_features, b.text_features, torch.tensor(10.0))
     assert "unsupported shape" in str(ei.value) and not lib.calls
+
+
+def _gloo_worker(rank, world, port, mode, q):
+    import os
+    import traceback
+
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        _cuda._DeviceGuard = _NoGuard
+        lib = _CallbackLib(_cuda.load_library())
+        losses._set_ops_for_testing(_PlumbingOps(lib, mn_major=(mode == "mn_major")))
+        b = make_spot_batch(n=256, d=128, k=8, seed=5).rank_slice(rank, world)
+        cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+                   neighbor_alpha_scale=0.5, float32_logits=True)
+        _step(SpatialLoss(**cfg, **({"precision": "fp32"} if mode == "fp32" else {})), b)
+        q.put((rank, list(lib.calls)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("mode", ["default", "fp32", "mn_major"])
+def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
+    """world_size 2: gathered operands, the single statistics-record exchange (scl_unpack_records with its pointer
+    tables) and, for W > 1, the transposed copies made in backward."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    from spatial_clip_b200 import build
+
+    build.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, mode, q), daemon=True) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    for r in range(2):
+        assert isinstance(got[r], list), got[r]
+    assert got[0] == got[1], "ranks must issue identical call sequences (collective order)"
+    calls = got[0]
+    assert calls.count("scl_unpack_records") == 1 and calls.count("scl_fwd_all") == 1 and calls.count("scl_bwd_dir") == 2
+    if mode == "fp32":
+        assert calls.count("scl_transpose_split") == 2
+    elif mode == "mn_major":
+        assert "scl_cast_bf16" not in calls
+    else:
+        assert calls.count("scl_cast_bf16") == 2  # transposed copies of the two gathered operands
