@@ -4,7 +4,7 @@
 #   gpurun --timeout 1200 -- 'bash scripts/r2_first_call.sh'
 mkdir -p gpurun_out
 echo "=== default parity"; timeout 400 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/r2_gpu_tests.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2_gpu_tests.log
-for t in 1 2 3; do
+for t in 1 2 3 7; do
   echo "=== SCL_BWD_TUNE=$t parity (bwd kernels, modules, mid/full size)"
   SCL_BWD_TUNE=$t timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
       -k "bwd_rows or modules_match or mid_size or full_size or wide" > gpurun_out/r2_tune${t}_tests.log 2>&1
@@ -26,7 +26,7 @@ except Exception as e:
     print("no json", e); print(open("gpurun_out/r2_bench_mn$mn.err").read()[-1500:])
 PY
 done
-for t in 0 1 2 3; do
+for t in 0 1 2 3 7; do
   echo "=== bench SCL_BWD_TUNE=$t"
   SCL_BWD_TUNE=$t timeout 300 python bench.py --steps 8 --warmup 3 > gpurun_out/r2_bench_tune$t.json 2> gpurun_out/r2_bench_tune$t.err
   python - <<PY

@@ -60,6 +60,7 @@ struct B2Bars {
 // kTune (developer knob SCL_BWD_TUNE, default 0; see profiles/r1_smem_port_accounting.md):
 //   bit 0: column coefficients / G tile through explicit shared-window LDS.128 / STS.128
 //   bit 1: epilogue barrier waits park with a suspend-time hint instead of re-polling every ~100 cycles
+//   bit 2: the same for the TMA-producer and MMA-issuer waits
 // kSplit = 1 is the fp32-accurate ("bf16x2") mode: every operand is a bf16 hi + lo pair.  The similarity is
 // contracted over the K-concatenated rows X' = (h|h|l), Y' = (h|l|h) of width 3 d (x.y ~= xh.yh + xh.yl + xl.yh,
 // the dropped terms are O(2^-18)), G is written as two bf16 tiles G1 + G2 and the gradient GEMM runs three passes
@@ -149,7 +150,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
       auto acquire = [&](int bytes_per_cta) {
         const int s = ring_s;
-        mbar_wait_t(&bars.empty[s], ring_ph ^ 1, timed, w_empty);
+        if constexpr ((kTune & 4) != 0) mbar_wait_hint(&bars.empty[s], ring_ph ^ 1, 2000u);
+        else mbar_wait_t(&bars.empty[s], ring_ph ^ 1, timed, w_empty);
         if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
         if (++ring_s == kB2Stages) {
           ring_s = 0;
@@ -160,7 +162,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
         const int cb = lt & 1;
-        mbar_wait_t(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, timed, w_ce);
+        if constexpr ((kTune & 4) != 0) mbar_wait_hint(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, 2000u);
+        else mbar_wait_t(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, timed, w_ce);
         mbar_arrive_expect_tx(&bars.coef_full[cb], kB2CoefBytes);
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
@@ -225,6 +228,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
       long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
+      auto mma_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if constexpr ((kTune & 4) != 0) {
+          mbar_wait_hint(bar, parity, 1000u);
+          __syncwarp();
+        } else {
+          mbar_wait_warp(bar, parity, timed, acc);
+        }
+      };
       if (!stream_x) mbar_wait_warp(&bars.x_full, 0, timed, w_x);
       tc_fence_after();
       int ring_s = 0;
@@ -237,14 +248,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       };
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
-        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
+        mma_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
         const int kstep = stream_x ? 1 : 2;
         for (int kc = 0; kc < nk; kc += kstep, advance()) {
           const int nb = min(kstep, nk - kc);
           const int s = ring_s;
-          mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fz);
+          mma_wait(&bars.full[s], ring_ph, w_fz);
           tc_fence_after();
           if (elect_one()) {
             for (int b = 0; b < nb; ++b) {
@@ -263,7 +274,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
       };
       auto issue_acc = [&](int lt) {
-        mbar_wait_warp(&bars.g_full, lt & 1, timed, w_gf);
+        mma_wait(&bars.g_full, lt & 1, w_gf);
         tc_fence_after();
         const int n_units = 4 * ng;
         constexpr int n_pass = kSplit ? 3 : 1;
@@ -272,7 +283,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           for (int u = 0; u < n_units; u += 2, advance()) {
             const int nb = min(2, n_units - u);
             const int s = ring_s;
-            mbar_wait_warp(&bars.full[s], ring_ph, timed, w_fy);
+            mma_wait(&bars.full[s], ring_ph, w_fy);
             tc_fence_after();
             if (elect_one()) {
               for (int b = 0; b < nb; ++b) {
@@ -554,10 +565,10 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
                                            diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
   static const int tune = [] {  // developer knob, read once per process
     const char* e = std::getenv("SCL_BWD_TUNE");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 0;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : 0;
   }();
   if (bwd_pair_mn_major())
-    return tune == 3 ? launch_bwd_rows_pair_t<3, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
+    return tune >= 3 ? launch_bwd_rows_pair_t<3, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
                                                        tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
                                                        dx_partial, dbg_t, stream)
                      : launch_bwd_rows_pair_t<0, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
@@ -570,7 +581,9 @@ cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& 
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
     case 3: return launch_bwd_rows_pair_t<3, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
                                              diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    default: break;
+    case 7: return launch_bwd_rows_pair_t<7, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                                diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    default: break;  // (4, 5, 6 are not instantiated)
   }
   return launch_bwd_rows_pair_t<0, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
                                    scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
