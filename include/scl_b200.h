@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SCL_ABI_VERSION 5
+#define SCL_ABI_VERSION 6
 #define SCL_OK 0
 #define SCL_ERR_INVALID_ARG (-1)
 #define SCL_ERR_UNSUPPORTED_SHAPE (-2)
@@ -177,6 +177,10 @@ typedef struct scl_fwd_args {
   void* workspace; size_t workspace_bytes;                 /* >= scl_fwd_workspace_bytes(...)               */
   int32_t* ranks_out;                                      /* NULL, or int32[b_local]: image -> gene retrieval ranks
                                                               in the local block (scl_fwd_rowstats_ranks)      */
+  int phases;                                              /* 0 = all; bit 0 soft targets (needs the gathered ids),
+                                                              bit 1 image-rows pass (needs txt_all), bit 2 text-rows
+                                                              pass + reductions (needs img_all): one call per phase
+                                                              lets the caller overlap the three all-gathers       */
 } scl_fwd_args;
 size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant);
 int scl_fwd_all(const scl_fwd_args* a, void* stream);

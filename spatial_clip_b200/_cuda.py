@@ -41,7 +41,8 @@ class FwdArgs(C.Structure):
                 ("txt_ids_all", _VP), ("nbr_ids", _VP), ("nbr_alpha", _VP), ("k", _I), ("alpha_scale", _F),
                 ("same_ids", _I), ("c", _F), ("w", _F), ("finalize_scalars", _I), ("col_it", _VP), ("w_it", _VP),
                 ("q_it", _VP), ("col_ti", _VP), ("w_ti", _VP), ("q_ti", _VP), ("stats_i", _VP), ("stats_t", _VP),
-                ("sums6", _VP), ("out4", _VP), ("workspace", _VP), ("workspace_bytes", _SZ), ("ranks_out", _VP)]
+                ("sums6", _VP), ("out4", _VP), ("workspace", _VP), ("workspace_bytes", _SZ), ("ranks_out", _VP),
+                ("phases", _I)]
 
 
 class BwdArgs(C.Structure):
@@ -115,7 +116,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 5:
+    if lib.scl_abi_version() != 6:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -160,6 +161,9 @@ class CudaOps:
         # developer knob (read by the library too): the gradient GEMM takes Y itself as an MN-major operand, so no
         # transposed copies are made or passed (bf16 mode, CTA-pair kernels only; not yet run on a B200)
         self.mn_major = os.environ.get("SCL_BWD_MN") == "1"
+        # developer knob (host side only): at W > 1 issue the feature / id exchanges without waiting and run the forward
+        # in three phases (scl_fwd_args.phases), each behind the wait of the one operand it reads (losses.py)
+        self.overlap_gather = os.environ.get("SCL_OVERLAP_GATHER") == "1"
 
     def _cycles(self, name, plan, like):
         """Developer timing mode: a zeroed int64 buffer (16 counters per CTA) when self.cycle_buffers is a dict."""
@@ -359,10 +363,13 @@ class CudaOps:
         return img, txt, img, txt, img_t, txt_t, scal
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars, want_ranks=False):
+                    finalize_scalars, want_ranks=False, waits=None):
         """Soft targets + both fused similarity/LSE passes + reductions: scl_fwd_all.
         ids = None (plain CLIP) or (img_ids_all, txt_ids_all, nbr_ids, nbr_alpha, same_ids).
-        want_ranks: also count, in the image-rows pass, each row's in-batch retrieval rank (self.last_ranks)."""
+        want_ranks: also count, in the image-rows pass, each row's in-batch retrieval rank (self.last_ranks).
+        waits = (wait_ids or None, wait_txt_all, wait_img_all): the gathered operands are still in flight; the call is
+        then issued once per phase (soft targets / image-rows pass / text-rows pass + reductions), each right after
+        the wait for the one operand that phase reads."""
         st = self._stream(img_l)
         n, d = img_all.shape
         kp1 = k + 1
@@ -387,13 +394,20 @@ class CudaOps:
                     _ptr(ids[2]) if ids else None, _ptr(ids[3]) if ids else None, k, float(alpha_scale), int(same),
                     float(c), float(w), int(finalize_scalars), _ptr(col_it), _ptr(w_it), _ptr(q_it), _ptr(col_ti),
                     _ptr(w_ti), _ptr(q_ti), _ptr(stats_i), _ptr(stats_t), _ptr(sums6), _ptr(out4), _ptr(ws), ws_bytes,
-                    None)
+                    None, 0)
         ranks = None
         if want_ranks:
             ranks = torch.empty((b_local,), dtype=torch.int32, device=dev)
             a.ranks_out = _ptr(ranks)
         with _DeviceGuard(dev):
-            self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
+            if waits is None:
+                self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
+            else:
+                for phase, wait in zip((1, 2, 4), waits):
+                    if wait is not None:
+                        wait()
+                    a.phases = phase
+                    self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
         self.launches += (3 if k > 0 else 1) * (1 if same else 2) + 5 + (1 if finalize_scalars else 0) + \
             (2 if want_ranks else 0)
         return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks

@@ -386,15 +386,21 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   char* rank_ws = ws + 2 * partial_bytes + (a->k > 0 ? align256(hash_bytes) : 0);
   int32_t* rank_partial = reinterpret_cast<int32_t*>(rank_ws);
   float* diag_z = reinterpret_cast<float*>(rank_ws + align256(static_cast<size_t>(p.n_slots) * p.m_pad * 4));
-  // soft targets: image rows use the text-id map, text rows the image-id map (losses.py:102-108)
-  rc = scl_build_positives(a->txt_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
-                           a->rank, a->k > 0 ? hash : nullptr, hash_bytes, a->col_it, a->w_it, a->q_it, stream);
-  if (rc != SCL_OK) return rc;
-  if (!a->same_ids && a->k > 0) {
-    rc = scl_build_positives(a->img_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
-                             a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti, stream);
+  // phases (0 = everything): 1 soft targets (needs the gathered ids), 2 image-rows pass (needs txt_all),
+  // 4 text-rows pass + reductions (needs img_all) -- separate calls let the caller overlap the exchanges
+  const int phases = a->phases == 0 ? 7 : a->phases;
+  if (phases & 1) {
+    // soft targets: image rows use the text-id map, text rows the image-id map (losses.py:102-108)
+    rc = scl_build_positives(a->txt_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k, a->alpha_scale,
+                             a->rank, a->k > 0 ? hash : nullptr, hash_bytes, a->col_it, a->w_it, a->q_it, stream);
     if (rc != SCL_OK) return rc;
+    if (!a->same_ids && a->k > 0) {
+      rc = scl_build_positives(a->img_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k,
+                               a->alpha_scale, a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti, stream);
+      if (rc != SCL_OK) return rc;
+    }
   }
+  if (phases & 2) {
   if (a->ranks_out != nullptr)  // image -> gene retrieval ranks within the local block, counted in the same pass
     rc = scl_fwd_rowstats_ranks(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i,
                                 a->rank * a->b_local, diag_z, rank_partial, a->ranks_out, stream);
@@ -405,6 +411,8 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1, a->stats_i,
                         stream);
   if (rc != SCL_OK) return rc;
+  }
+  if (!(phases & 4)) return SCL_OK;
   rc = scl_fwd_rowstats(a->txt_l, a->b_local, a->img_all, a->n_global, a->d, a->scalars3, &p, part_t, nullptr, 0,
                         nullptr, stream);
   if (rc != SCL_OK) return rc;

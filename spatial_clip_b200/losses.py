@@ -82,6 +82,17 @@ def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
     return out.view(t.dtype).reshape((world * t.shape[0],) + tuple(t.shape[1:]))
 
 
+def _all_gather_rows_async(t: torch.Tensor, world: int, group):
+    """Non-blocking form of ``_all_gather_rows``: returns (gathered tensor, wait).  ``wait()`` makes the current
+    stream (NCCL) / the caller (gloo) wait for THIS exchange only, so later exchanges keep running underneath the
+    kernels that need only this one."""
+    t = t.contiguous()
+    carrier = t.view(torch.uint8).reshape(-1)
+    out = torch.empty(world * carrier.numel(), dtype=torch.uint8, device=t.device)
+    work = dist.all_gather_into_tensor(out, carrier, group=group, async_op=True)
+    return out.view(t.dtype).reshape((world * t.shape[0],) + tuple(t.shape[1:])), work.wait
+
+
 @dataclass
 class _Cfg:
     kind: str  # "spatial" | "clip"
@@ -135,7 +146,15 @@ class _ContrastiveLossFn(torch.autograd.Function):
         img_l, txt_l, img_c, txt_c, img_t, txt_t, scalars = ops.prepare(
             image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap,
             fuse_t and ctx.needs_input_grad[1], fuse_t and ctx.needs_input_grad[0], ld_t, split=cfg.split)
-        if world > 1:
+        # Developer knob (SCL_OVERLAP_GATHER=1, W > 1): the exchanges are issued back to back without waiting -- gene
+        # features, tile ids, image features -- and the forward runs in three phases, each waiting only for the
+        # operand it reads, so the image-feature exchange runs underneath the image-rows pass (which needs only the
+        # gathered gene features).  Same collectives in the same order on every rank; off until run on a B200.
+        overlap = world > 1 and getattr(ops, "overlap_gather", False)
+        waits = None
+        if overlap:
+            txt_all, wait_txt = _all_gather_rows_async(txt_c, world, cfg.group)
+        elif world > 1:
             img_all = _all_gather_rows(img_c, world, cfg.group)
             txt_all = _all_gather_rows(txt_c, world, cfg.group)
         else:
@@ -150,13 +169,23 @@ class _ContrastiveLossFn(torch.autograd.Function):
                         and image_tile_ids.shape == text_tile_ids.shape)
             img_ids = image_tile_ids.to(torch.int64).contiguous()
             txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
-            if world > 1:
+            if overlap:
+                img_ids_all, wait_ids = _all_gather_rows_async(img_ids, world, cfg.group)
+                if same_ids:
+                    txt_ids_all = img_ids_all
+                else:
+                    txt_ids_all, wait_ids2 = _all_gather_rows_async(txt_ids, world, cfg.group)
+                    wait_ids = (lambda a=wait_ids, b=wait_ids2: (a(), b()))
+            elif world > 1:
                 img_ids_all = _all_gather_rows(img_ids, world, cfg.group)
                 txt_ids_all = img_ids_all if same_ids else _all_gather_rows(txt_ids, world, cfg.group)
             else:
                 img_ids_all, txt_ids_all = img_ids, txt_ids
             ids = (img_ids_all, txt_ids_all, neighbor_tile_ids.to(torch.int64).contiguous(),
                    neighbor_alphas.to(torch.float32).contiguous(), same_ids)
+        if overlap:
+            img_all, wait_img = _all_gather_rows_async(img_c, world, cfg.group)
+            waits = (wait_ids if ids is not None else None, wait_txt, wait_img)
 
         # ---- soft targets (losses.py:91-111), both fused similarity + online-LSE passes (losses.py:78-89,
         # 113-121), row reductions and the loss scalars: one host call
@@ -164,7 +193,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         c = 0.5 / (n if global_clip else b_local)
         (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
             img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
-            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks)
+            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}))
         if ranks is None:
             ranks = torch.empty((0,), dtype=torch.int32, device=dev)
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)

@@ -120,15 +120,26 @@ class EmulatedOps:
         return y_t
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars, want_ranks=False):
+                    finalize_scalars, want_ranks=False, waits=None):
+        # waits (overlapped exchanges): each phase may only touch the operand whose wait has been called -- the
+        # checker poisons nothing, but it calls the waits exactly where the CUDA backend does
+        wait_ids, wait_txt, wait_img = waits if waits is not None else (None, None, None)
+        if waits is not None:
+            self.calls.append("forward_all_phased")
+        if wait_ids is not None:
+            wait_ids()
         if ids is None:
             it = ti = self.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
         else:
             img_ids_all, txt_ids_all, nbr, alpha, same = ids
             it = self.build_positives(txt_ids_all, nbr, alpha, b_local, k, alpha_scale, rank, img_l)
             ti = it if same else self.build_positives(img_ids_all, nbr, alpha, b_local, k, alpha_scale, rank, img_l)
+        if wait_txt is not None:
+            wait_txt()
         part_i, plan_i = self.fwd_rowstats(img_l, txt_all, scalars)
         stats_i = self.row_finalize(part_i, plan_i, img_l, txt_all, it[0], it[2])
+        if wait_img is not None:
+            wait_img()
         part_t, plan_t = self.fwd_rowstats(txt_l, img_all, scalars)
         stats_t = self.row_finalize(part_t, plan_t, txt_l, img_all, ti[0], ti[2])
         sums6 = self.reduce_rows(stats_i, stats_t, scalars)

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_plans_and_errors_without_gpu(lib):
     from spatial_clip_b200._cuda import SclPlan
 
-    assert lib.scl_abi_version() == 5
+    assert lib.scl_abi_version() == 6
     p = SclPlan()
     assert lib.scl_fwd_plan(4096, 32768, 512, 0, ctypes.byref(p)) == 0
     assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.variant == 0 and p.chunks * p.tiles_per_chunk >= 32768 // 256

@@ -36,8 +36,9 @@ class _CallbackLib:
 
 
 class _PlumbingOps(_cuda.CudaOps):
-    def __init__(self, lib, mn_major=False):
+    def __init__(self, lib, mn_major=False, overlap_gather=False):
         self.lib = lib
+        self.overlap_gather = overlap_gather
         self._checked = set()
         self.variant = 1
         self.launches = 0
@@ -149,7 +150,7 @@ def _gloo_worker(rank, world, port, mode, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         _cuda._DeviceGuard = _NoGuard
         lib = _CallbackLib(_cuda.load_library())
-        losses._set_ops_for_testing(_PlumbingOps(lib, mn_major=(mode == "mn_major")))
+        losses._set_ops_for_testing(_PlumbingOps(lib, mn_major=(mode == "mn_major"), overlap_gather=(mode == "overlap")))
         b = make_spot_batch(n=256, d=128, k=8, seed=5).rank_slice(rank, world)
         cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
                    neighbor_alpha_scale=0.5, float32_logits=True)
@@ -161,7 +162,7 @@ def _gloo_worker(rank, world, port, mode, q):
         q.put((rank, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("mode", ["default", "fp32", "mn_major"])
+@pytest.mark.parametrize("mode", ["default", "fp32", "mn_major", "overlap"])
 def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
     """world_size 2: gathered operands, the single statistics-record exchange (scl_unpack_records with its pointer
     tables) and, for W > 1, the transposed copies made in backward."""
@@ -187,7 +188,9 @@ def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
         assert isinstance(got[r], list), got[r]
     assert got[0] == got[1], "ranks must issue identical call sequences (collective order)"
     calls = got[0]
-    assert calls.count("scl_unpack_records") == 1 and calls.count("scl_fwd_all") == 1 and calls.count("scl_bwd_dir") == 2
+    # overlapped exchanges: one scl_fwd_all call per phase (soft targets / image-rows pass / text-rows pass)
+    assert calls.count("scl_fwd_all") == (3 if mode == "overlap" else 1)
+    assert calls.count("scl_unpack_records") == 1 and calls.count("scl_bwd_dir") == 2
     if mode == "fp32":
         assert calls.count("scl_transpose_split") == 2
     elif mode == "mn_major":

@@ -163,17 +163,21 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, name, q, round_bf16=False):
+def _worker(rank, world, port, name, q, round_bf16=False, overlap=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        losses._set_ops_for_testing(EmulatedOps(round_bf16=round_bf16))
+        ops = EmulatedOps(round_bf16=round_bf16)
+        ops.overlap_gather = overlap  # the SCL_OVERLAP_GATHER=1 route: non-blocking exchanges, phased forward
+        losses._set_ops_for_testing(ops)
         meta, _ = load_golden(name)
         mod = _build(meta)  # rank / world resolved lazily from the process group
         assert (mod.rank, mod.world_size) == (rank, world)
-        q.put((rank,) + _run_rank(meta, rank, world, mod))
+        res = _run_rank(meta, rank, world, mod)
+        assert ("forward_all_phased" in ops.calls) == overlap
+        q.put((rank,) + res)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -190,6 +194,28 @@ def test_gloo_ranks_match_reference(name):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = meta["gen"]["n"] // world
+    for rank, loss, gi, gt, ds in got:
+        _assert_close(gold, rank, b, loss, gi, gt, ds, meta["scale"])
+
+
+@pytest.mark.parametrize("name", ["spatial_n256_w2", "spatial_n256_w4_ll0_gwg1", "clip_n128_w2_ll1_gwg1",
+                                  "clip_n128_w4_ll0_gwg0"])
+def test_gloo_overlapped_exchanges_match_reference(name):
+    """SCL_OVERLAP_GATHER route: exchanges issued without waiting (gene features, ids, image features), forward in
+    three phases each behind its own wait -- same results as the blocking route."""
+    meta, gold = load_golden(name)
+    world = meta["world"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q, False, True)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=240) for _ in range(world)]
