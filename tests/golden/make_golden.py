@@ -98,8 +98,12 @@ def run_spatial(ref_mod, cls_name, batch, scale, world, ctor, logit_bias=None, c
             captured.append(x.detach().clone().numpy())
         return real_normalize(x, p=p, dim=dim, **kw)
 
+    gather_calls = [0]
+
     def fake_all_gather(lst, t):
-        src = ids
+        # the reference gathers the image-side ids first, then the text-side ids (losses.py:63-68)
+        src = ids if (text_ids is None or gather_calls[0] % 2 == 0) else text_ids
+        gather_calls[0] += 1
         for q in range(world):
             lst[q] = src[q * b:(q + 1) * b].clone()
 
@@ -211,6 +215,18 @@ def main():
         add("spatial_n96_asym_text_ids", "spatial", gasym, 30.0, 1, SPATIAL_DEFAULT,
             run_spatial(ref, "SpatialLoss", ba, 30.0, 1, SPATIAL_DEFAULT, capture_labels=True,
                         text_ids=shuffled_text_ids(ba.tile_ids, 77)), text_ids_seed=77)
+        idx = json.loads((OUT / "index.json").read_text())
+        idx.update(cases)
+        (OUT / "index.json").write_text(json.dumps(idx, indent=1, sort_keys=True))
+        return
+
+    if len(sys.argv) > 1 and sys.argv[1] == "--asym-w2-only":
+        # as above, over two ranks: the TEXT-side ids travel through the second id all-gather (losses.py:63-68)
+        gasym = dict(n=192, d=64, k=8, seed=1009, dup_frac=0.05, self_loops=True)
+        ba = make_spot_batch(**gasym)
+        add("spatial_n192_w2_asym_text_ids", "spatial", gasym, 30.0, 2, SPATIAL_DEFAULT,
+            run_spatial(ref, "SpatialLoss", ba, 30.0, 2, SPATIAL_DEFAULT,
+                        text_ids=shuffled_text_ids(ba.tile_ids, 78)), text_ids_seed=78)
         idx = json.loads((OUT / "index.json").read_text())
         idx.update(cases)
         (OUT / "index.json").write_text(json.dumps(idx, indent=1, sort_keys=True))

@@ -33,14 +33,17 @@ def _build(meta, rank=None, world=None):
 
 
 def _run_rank(meta, rank, world, mod):
-    b = make_spot_batch(**meta["gen"]).rank_slice(rank, world)
+    full = make_spot_batch(**meta["gen"])
+    b = full.rank_slice(rank, world)
+    bl = b.tile_ids.shape[0]
+    txt_ids = text_ids_for(meta, full)[rank * bl:(rank + 1) * bl]  # text-side ids are defined on the GLOBAL batch
     img = b.image_features.clone().requires_grad_(True)
     txt = b.text_features.clone().requires_grad_(True)
     s = torch.tensor(float(meta["scale"]), requires_grad=True)
     bias = torch.tensor(meta["logit_bias"]) if "logit_bias" in meta else None
     if meta["kind"] == "spatial":
         out = mod(image_features=img, text_features=txt, logit_scale=s, image_tile_ids=b.tile_ids,
-                  text_tile_ids=text_ids_for(meta, b), neighbor_tile_ids=b.neighbor_tile_ids,
+                  text_tile_ids=txt_ids, neighbor_tile_ids=b.neighbor_tile_ids,
                   neighbor_alphas=b.neighbor_alphas, logit_bias=bias)
     else:
         out = mod(image_features=img, text_features=txt, logit_scale=s, logit_bias=bias)
