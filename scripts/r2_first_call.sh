@@ -45,6 +45,9 @@ echo "exit $?"; tail -2 gpurun_out/r2_asym_tests.log
 echo "=== in-pass retrieval ranks"
 SCL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_retrieval_ranks.py -m gpu -q -p no:cacheprovider > gpurun_out/r2_ranks_tests.log 2>&1
 echo "exit $?"; tail -2 gpurun_out/r2_ranks_tests.log
+echo "=== data-side soft targets (SpatialLossFromColumns, phases = 6)"
+SCL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_positive_columns.py -m gpu -q -p no:cacheprovider > gpurun_out/r2_columns_tests.log 2>&1
+echo "exit $?"; tail -2 gpurun_out/r2_columns_tests.log
 echo "=== fp32-accurate mode (precision=fp32): parity, then speed"
 SCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_fp32_mode.py -m gpu -q -p no:cacheprovider -s > gpurun_out/r2_fp32_tests.log 2>&1
 echo "exit $?"; grep -E "passed|failed" gpurun_out/r2_fp32_tests.log | tail -2; grep -E "^(FAILED|ERROR|E  +Assert|E  +assert|E  +.*Error)" gpurun_out/r2_fp32_tests.log | cut -c1-240 | head -20

@@ -3,7 +3,7 @@
 Public API mirrors the reference's loss modules (see losses.py); the compute is CUDA-only behind the
 C ABI declared in include/scl_b200.h.
 """
-from .losses import ClipLoss, GlobalMappingMultiPositiveClipLoss, SpatialLoss  # noqa: F401
+from .losses import ClipLoss, GlobalMappingMultiPositiveClipLoss, SpatialLoss, SpatialLossFromColumns  # noqa: F401
 
-__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss"]
+__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss", "SpatialLossFromColumns"]
 __version__ = "0.1.0"

@@ -363,24 +363,35 @@ class CudaOps:
         return img, txt, img, txt, img_t, txt_t, scal
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars, want_ranks=False, waits=None):
+                    finalize_scalars, want_ranks=False, waits=None, positives=None):
         """Soft targets + both fused similarity/LSE passes + reductions: scl_fwd_all.
         ids = None (plain CLIP) or (img_ids_all, txt_ids_all, nbr_ids, nbr_alpha, same_ids).
         want_ranks: also count, in the image-rows pass, each row's in-batch retrieval rank (self.last_ranks).
         waits = (wait_ids or None, wait_txt_all, wait_img_all): the gathered operands are still in flight; the call is
         then issued once per phase (soft targets / image-rows pass / text-rows pass + reductions), each right after
-        the wait for the one operand that phase reads."""
+        the wait for the one operand that phase reads.
+        positives = (col, w, q) int32 / fp32 / fp32 [B_l, K+1] of the image rows (+ the same three of the text rows):
+        soft targets resolved on the data side; the builder phase is skipped."""
         st = self._stream(img_l)
         n, d = img_all.shape
         kp1 = k + 1
         dev = img_l.device
         same = ids is None or ids[4]
-        lists = torch.empty((2 if not same else 1, 3, b_local, kp1), dtype=torch.float32, device=dev)
-        col_it, w_it, q_it = lists[0, 0].view(torch.int32), lists[0, 1], lists[0, 2]
-        if same:
-            col_ti, w_ti, q_ti = col_it, w_it, q_it
+        if positives is not None:
+            for t in positives:
+                if t.device != dev or not t.is_contiguous() or tuple(t.shape) != (b_local, kp1):
+                    raise SclError("precomputed soft-target lists must be contiguous [B_l, K+1] tensors on the "
+                                   "features' device")
+            col_it, w_it, q_it = positives[:3]
+            col_ti, w_ti, q_ti = positives[3:6] if len(positives) >= 6 else positives[:3]
+            same = len(positives) < 6
         else:
-            col_ti, w_ti, q_ti = lists[1, 0].view(torch.int32), lists[1, 1], lists[1, 2]
+            lists = torch.empty((2 if not same else 1, 3, b_local, kp1), dtype=torch.float32, device=dev)
+            col_it, w_it, q_it = lists[0, 0].view(torch.int32), lists[0, 1], lists[0, 2]
+            if same:
+                col_ti, w_ti, q_ti = col_it, w_it, q_it
+            else:
+                col_ti, w_ti, q_ti = lists[1, 0].view(torch.int32), lists[1, 1], lists[1, 2]
         small = torch.empty((2 * b_local + 3, 4), dtype=torch.float32, device=dev)
         stats_i, stats_t = small[:b_local], small[b_local:2 * b_local]
         sums6 = small[2 * b_local:2 * b_local + 2].reshape(-1)[:6]
@@ -401,15 +412,18 @@ class CudaOps:
             a.ranks_out = _ptr(ranks)
         with _DeviceGuard(dev):
             if waits is None:
+                a.phases = 6 if positives is not None else 0  # 6: both similarity passes, no soft-target builder
                 self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
             else:
                 for phase, wait in zip((1, 2, 4), waits):
                     if wait is not None:
                         wait()
+                    if phase == 1 and positives is not None:
+                        continue
                     a.phases = phase
                     self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
-        self.launches += (3 if k > 0 else 1) * (1 if same else 2) + 5 + (1 if finalize_scalars else 0) + \
-            (2 if want_ranks else 0)
+        built = 0 if positives is not None else (3 if k > 0 else 1) * (1 if same else 2)
+        self.launches += built + 5 + (1 if finalize_scalars else 0) + (2 if want_ranks else 0)
         return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks
 
     def backward_dir(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,

@@ -40,7 +40,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss"]
+__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss", "SpatialLossFromColumns"]
 
 _OPS = None
 
@@ -124,7 +124,7 @@ def _col_mode(cfg: _Cfg) -> int:
 class _ContrastiveLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, image_tile_ids, text_tile_ids, neighbor_tile_ids,
-                neighbor_alphas, cfg: _Cfg):
+                neighbor_alphas, cfg: _Cfg, positives=None):
         ops = _ops()
         b_local, d = image_features.shape
         world, rank = cfg.world, cfg.rank
@@ -163,7 +163,11 @@ class _ContrastiveLossFn(torch.autograd.Function):
         # ---- tile ids (losses.py:63-68); plain CLIP has only the diagonal
         ids = None
         k = 0
-        if cfg.kind == "spatial":
+        if positives is not None:
+            # soft targets resolved on the data side (positives.py): (columns int32, weights, probs) [B_l, K+1] of the
+            # image rows, optionally followed by the same three for the text rows.  No id exchange, no hash build.
+            k = positives[0].shape[1] - 1
+        elif cfg.kind == "spatial":
             k = neighbor_tile_ids.shape[1]
             same_ids = (image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
                         and image_tile_ids.shape == text_tile_ids.shape)
@@ -193,7 +197,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
         c = 0.5 / (n if global_clip else b_local)
         (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
             img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
-            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}))
+            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}),
+            **({"positives": positives} if positives is not None else {}))
         if ranks is None:
             ranks = torch.empty((0,), dtype=torch.int32, device=dev)
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
@@ -210,6 +215,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ctx.transposed = (img_t, txt_t)  # None unless produced above
         ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
                               q_ti)
+        if positives is not None:  # the caller already holds them: do not hand inputs back as outputs
+            col_it, w_it, q_it = (t.new_empty((0,)) for t in (col_it, w_it, q_it))
         ctx.mark_non_differentiable(col_it, w_it, q_it, ranks)
         return out4[0].clone(), col_it, w_it, q_it, ranks
 
@@ -260,7 +267,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)
-        return d_img, d_txt, d_scale, None, None, None, None, None
+        return d_img, d_txt, d_scale, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,6 +359,55 @@ class SpatialLoss(_LossBase):
                                                           image_tile_ids, text_tile_ids, neighbor_tile_ids,
                                                           neighbor_alphas, cfg)
         self.last_positives = (col, w, q)
+        self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
+        return {"contrastive_loss": loss}
+
+
+class SpatialLossFromColumns(SpatialLoss):
+    """``SpatialLoss`` fed with soft targets that the data pipeline already resolved to global columns
+    (producer: ``spatial_clip_b200.positives.resolve_positive_columns`` at collate time).
+
+    Same constructor and same arithmetic as ``SpatialLoss`` (reference: losses.py:11-124); ``forward`` takes
+    ``positive_columns`` int32 / ``positive_probs`` fp32 ``[B_l, K+1]`` (slot 0 = the row's own column) instead of the
+    four id / neighbour tensors, so the two id all-gathers (losses.py:63-68), the id -> column map and the label loop
+    (losses.py:91-111) leave the step altogether.  ``neighbor_alpha_scale`` is applied by the producer, not here.
+    ``positive_*_text`` are the text-row lists when the two id vectors differ (the reference's loader makes them
+    equal).  The LightningModule dispatches by parameter name (spatial_clip_module.py:44,58-61), so a collate that
+    adds these keys (``positives.collate_positive_columns``) is all the integration needs."""
+
+    def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
+                positive_columns: torch.Tensor, positive_probs: torch.Tensor,
+                positive_weights: Optional[torch.Tensor] = None, positive_columns_text: Optional[torch.Tensor] = None,
+                positive_probs_text: Optional[torch.Tensor] = None, logit_bias: Optional[torch.Tensor] = None,
+                output_dict: bool = True) -> Dict[str, torch.Tensor]:
+        self._check_features(image_features, text_features, logit_bias)
+        b = image_features.shape[0]
+        if positive_columns.dim() != 2 or positive_columns.shape[0] != b or \
+                positive_probs.shape != positive_columns.shape:
+            raise ValueError("positive_columns / positive_probs must both be [B, K+1]")
+        if (positive_columns_text is None) != (positive_probs_text is None):
+            raise ValueError("positive_columns_text and positive_probs_text go together")
+        dev = image_features.device
+
+        def prep(col, q, w):
+            col = col.to(device=dev, dtype=torch.int32).contiguous()
+            q = q.to(device=dev, dtype=torch.float32).contiguous()
+            w = q if w is None else w.to(device=dev, dtype=torch.float32).contiguous()
+            return col, w, q
+
+        pos = prep(positive_columns, positive_probs, positive_weights)
+        if positive_columns_text is not None:
+            if positive_columns_text.shape != positive_columns.shape or \
+                    positive_probs_text.shape != positive_columns.shape:
+                raise ValueError("text-row lists must have the shape of the image-row lists")
+            pos = pos + prep(positive_columns_text, positive_probs_text, None)
+        cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
+                   self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
+                   self.precision == "fp32", self.track_retrieval_ranks)
+        loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,
+                                                        self._scale_tensor(logit_scale, image_features), None, None,
+                                                        None, None, cfg, pos)
+        self.last_positives = pos[:3]
         self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
         return {"contrastive_loss": loss}
 

@@ -120,7 +120,7 @@ class EmulatedOps:
         return y_t
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
-                    finalize_scalars, want_ranks=False, waits=None):
+                    finalize_scalars, want_ranks=False, waits=None, positives=None):
         # waits (overlapped exchanges): each phase may only touch the operand whose wait has been called -- the
         # checker poisons nothing, but it calls the waits exactly where the CUDA backend does
         wait_ids, wait_txt, wait_img = waits if waits is not None else (None, None, None)
@@ -128,7 +128,11 @@ class EmulatedOps:
             self.calls.append("forward_all_phased")
         if wait_ids is not None:
             wait_ids()
-        if ids is None:
+        if positives is not None:  # resolved on the data side: the builder is skipped
+            self.calls.append("forward_all_precomputed")
+            it = tuple(positives[:3])
+            ti = tuple(positives[3:6]) if len(positives) >= 6 else it
+        elif ids is None:
             it = ti = self.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
         else:
             img_ids_all, txt_ids_all, nbr, alpha, same = ids

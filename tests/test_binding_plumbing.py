@@ -17,6 +17,7 @@ HOST_ONLY = {"scl_abi_version", "scl_error_string", "scl_fwd_plan", "scl_bwd_pla
 class _CallbackLib:
     def __init__(self, real):
         self.calls = []
+        self.fwd_phases = []
         self._keep = []
         for name, (res, args) in _cuda.EXPORTS.items():
             if name in HOST_ONLY:
@@ -27,6 +28,8 @@ class _CallbackLib:
             def make(nm):
                 def cb(*a):
                     self.calls.append(nm)
+                    if nm == "scl_fwd_all":  # which phases of the composite forward were asked for
+                        self.fwd_phases.append(C.cast(a[0], C.POINTER(_cuda.FwdArgs)).contents.phases)
                     return 0
                 return cb
 
@@ -197,3 +200,26 @@ def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
         assert "scl_cast_bf16" not in calls
     else:
         assert calls.count("scl_cast_bf16") == 2  # transposed copies of the two gathered operands
+
+
+def test_precomputed_columns_skip_the_builder_phase(plumbing):
+    """SpatialLossFromColumns: one scl_fwd_all call with phases = 6 (both similarity passes, no soft-target builder),
+    the caller's int32 / fp32 lists go to the library as they are."""
+    from spatial_clip_b200 import SpatialLossFromColumns
+    from spatial_clip_b200.positives import resolve_positive_columns
+
+    ops, lib = plumbing()
+    b = make_spot_batch(n=300, d=128, k=8, seed=3)
+    col, w, q = resolve_positive_columns(b.tile_ids, b.neighbor_tile_ids, b.neighbor_alphas, 0.5)
+    img = b.image_features.clone().requires_grad_(True)
+    txt = b.text_features.clone().requires_grad_(True)
+    mod = SpatialLossFromColumns(cap_logit_scale=40.0, temp_reg_weight=0.05)
+    mod(img, txt, torch.tensor(30.0, requires_grad=True), positive_columns=col, positive_probs=q,
+        positive_weights=w)["contrastive_loss"].backward()
+    assert lib.calls.count("scl_fwd_all") == 1 and lib.fwd_phases == [6] and lib.calls.count("scl_bwd_dir") == 2
+    assert img.grad.shape == img.shape and mod.last_positives[0].dtype == torch.int32
+    # the ordinary route asks for everything in one call
+    lib.calls.clear()
+    lib.fwd_phases.clear()
+    _step(SpatialLoss(), b)
+    assert lib.fwd_phases == [0]
