@@ -526,6 +526,7 @@ bool bwd_pair_mn_major() {
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 127) / 128 * max(1, bwd_pair_d_slices(d));
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
+  if (const int c = chunks_override("SCL_BWD_CHUNKS", n_tiles, tiles_per_chunk)) return c;
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 

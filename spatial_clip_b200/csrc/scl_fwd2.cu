@@ -303,6 +303,7 @@ size_t fwd_pair_smem_bytes(int d) {
 int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
+  if (const int c = chunks_override("SCL_FWD_CHUNKS", n_tiles, tiles_per_chunk)) return c;
   return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -44,6 +45,18 @@ inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles
   }
   *tiles_per_chunk = best_tpc;
   return best_c;
+}
+// Developer knob: SCL_FWD_CHUNKS / SCL_BWD_CHUNKS = c > 0 overrides the picker of the CTA-pair kernels with (about) c
+// column chunks (plans and work-area sizes follow, they all go through the pickers).  Unset: the balanced choice.
+inline int chunks_override(const char* env_name, int n_tiles, int* tiles_per_chunk) {
+  const char* e = std::getenv(env_name);
+  if (e == nullptr || e[0] == 0) return 0;
+  const int c = std::atoi(e);
+  if (c <= 0) return 0;
+  const int cc = c < n_tiles ? c : n_tiles;
+  const int tpc = (n_tiles + cc - 1) / cc;
+  *tiles_per_chunk = tpc;
+  return (n_tiles + tpc - 1) / tpc;
 }
 size_t fwd_pair_smem_bytes(int d);
 int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
