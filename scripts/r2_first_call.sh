@@ -39,6 +39,21 @@ except Exception as e:
     print("no json", e); print(open("gpurun_out/r2_bench_tune$t.err").read()[-1500:])
 PY
 done
+echo "=== SCL_BWD_STREAMS=1 (gene-side backward chain on a second stream): parity, then speed with the one-call-per-phase route timed"
+SCL_BWD_STREAMS=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
+    -k "modules_match or bf16_inputs or mid_size or full_size or multi_rank" > gpurun_out/r2_streams_tests.log 2>&1
+echo "exit $?"; tail -2 gpurun_out/r2_streams_tests.log
+for st in 0 1; do
+  SCL_BWD_STREAMS=$st timeout 300 python bench.py --steps 8 --warmup 3 --kernel-events after > gpurun_out/r2_bench_streams$st.json 2> gpurun_out/r2_bench_streams$st.err
+  python - <<PY
+import json
+try:
+    j = json.load(open("gpurun_out/r2_bench_streams$st.json"))
+    print("SCL_BWD_STREAMS=$st ms/step", round(j["ms_per_step"], 3), "pairs/s", round(j["value"]), "e2e", round(j["e2e"]["value"]), "loss", j["loss"])
+except Exception as e:
+    print("no json", e); print(open("gpurun_out/r2_bench_streams$st.err").read()[-1500:])
+PY
+done
 echo "=== fixture with different image / text tile ids (added after the last B200 run)"
 SCL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k asym > gpurun_out/r2_asym_tests.log 2>&1
 echo "exit $?"; tail -2 gpurun_out/r2_asym_tests.log

@@ -2,10 +2,10 @@
 # Round-2 multi-GPU call (default 2 GPUs): what has not run on more than one B200 yet.
 #   gpurun --gpus 2 --timeout 900 -- 'bash scripts/r2_multi_gpu.sh 2'
 # 1. multi-rank parity (ranks share GPU 0, gloo transport) for the default route and the two W > 1 developer knobs
-# 2. bench.py under torchrun (NCCL) for: default | SCL_OVERLAP_GATHER=1 | SCL_BWD_MN=1 | both
+# 2. bench.py under torchrun (NCCL), one-call-per-phase route timed (--kernel-events after), for each knob and all together
 N=${1:-2}
 mkdir -p gpurun_out
-for knobs in "" "SCL_OVERLAP_GATHER=1" "SCL_BWD_MN=1"; do
+for knobs in "" "SCL_OVERLAP_GATHER=1" "SCL_BWD_MN=1" "SCL_BWD_STREAMS=1"; do
   tag=$(echo "${knobs:-default}" | tr '= ' '__')
   echo "=== multi-rank parity [$tag]"
   env $knobs timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k multi_rank \
@@ -13,12 +13,13 @@ for knobs in "" "SCL_OVERLAP_GATHER=1" "SCL_BWD_MN=1"; do
   echo "exit $?"; tail -2 gpurun_out/r2_mr_$tag.log
 done
 port=29500
-for knobs in "" "SCL_OVERLAP_GATHER=1" "SCL_BWD_MN=1" "SCL_OVERLAP_GATHER=1 SCL_BWD_MN=1 SCL_BWD_TUNE=3"; do
+for knobs in "" "SCL_OVERLAP_GATHER=1" "SCL_BWD_MN=1" "SCL_BWD_STREAMS=1" "SCL_BWD_CHUNKS=2" \
+             "SCL_OVERLAP_GATHER=1 SCL_BWD_MN=1 SCL_BWD_STREAMS=1 SCL_BWD_TUNE=3"; do
   tag=$(echo "${knobs:-default}" | tr '= ' '__')
   port=$((port + 1))
   echo "=== bench N=$N [$tag]"
   env $knobs timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-      --master-port $port bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n${N}_$tag.json 2> gpurun_out/r2_bench_n${N}_$tag.err
+      --master-port $port bench.py --gpus $N --steps 10 --warmup 3 --kernel-events after > gpurun_out/r2_bench_n${N}_$tag.json 2> gpurun_out/r2_bench_n${N}_$tag.err
   echo "exit $?"
   python - <<PY
 import json

@@ -164,6 +164,10 @@ class CudaOps:
         # developer knob (host side only): at W > 1 issue the feature / id exchanges without waiting and run the forward
         # in three phases (scl_fwd_args.phases), each behind the wait of the one operand it reads (losses.py)
         self.overlap_gather = os.environ.get("SCL_OVERLAP_GATHER") == "1"
+        # developer knob (host side only): the gene-side backward chain runs on a second stream next to the image-side
+        # one (losses.py); not with the per-kernel timing modes, which assume one stream
+        self.two_streams = os.environ.get("SCL_BWD_STREAMS") == "1"
+        self._side_streams = {}
 
     def _cycles(self, name, plan, like):
         """Developer timing mode: a zeroed int64 buffer (16 counters per CTA) when self.cycle_buffers is a dict."""
@@ -203,6 +207,15 @@ class CudaOps:
                 self._check(self.lib.scl_check_device(C.byref(n)), "scl_check_device")
             self._checked.add(idx)
         return torch.cuda.current_stream(t.device).cuda_stream
+
+    def side_stream(self, device):
+        """The second stream of `device` for the two-stream backward, or None when a per-kernel timing mode is on."""
+        if self.kernel_events is not None or getattr(self, "cycle_buffers", None) is not None:
+            return None
+        st = self._side_streams.get(device.index)
+        if st is None:
+            st = self._side_streams[device.index] = torch.cuda.Stream(device=device)
+        return st
 
     @staticmethod
     def empty(shape, dtype, like: torch.Tensor) -> torch.Tensor:

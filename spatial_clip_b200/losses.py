@@ -250,20 +250,47 @@ class _ContrastiveLossFn(torch.autograd.Function):
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_scale = None
         img_all_t, txt_all_t = ctx.transposed
-        if need_i:
-            if txt_all_t is None and not ctx.no_t:
-                txt_all_t = ops.transpose_split(txt_all, d, ld_t) if cfg.split else \
+
+        def grad_image():
+            t = txt_all_t
+            if t is None and not ctx.no_t:
+                t = ops.transpose_split(txt_all, d, ld_t) if cfg.split else \
                     ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
-            d_img = ops.backward_dir(img_l, txt_all, txt_all_t, stats_i, stats_t_all, col_it, q_it, col_ti_all,
-                                     q_ti_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
-                                     ctx.in_dtypes[0], q_ti, split=cfg.split)
-        if need_t:
-            if img_all_t is None and not ctx.no_t:
-                img_all_t = ops.transpose_split(img_all, d, ld_t) if cfg.split else \
+            return ops.backward_dir(img_l, txt_all, t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
+                                    b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0], q_ti,
+                                    split=cfg.split)
+
+        def grad_text():
+            t = img_all_t
+            if t is None and not ctx.no_t:
+                t = ops.transpose_split(img_all, d, ld_t) if cfg.split else \
                     ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
-            d_txt = ops.backward_dir(txt_l, img_all, img_all_t, stats_t, stats_i_all, col_ti, q_ti, col_it_all,
-                                     q_it_all, b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode,
-                                     ctx.in_dtypes[1], q_it, split=cfg.split)
+            return ops.backward_dir(txt_l, img_all, t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
+                                    b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1], q_it,
+                                    split=cfg.split)
+
+        side = ops.side_stream(img_l.device) if (need_i and need_t and getattr(ops, "two_streams", False)) else None
+        if side is not None:
+            # Developer knob (SCL_BWD_STREAMS=1): the two directions are independent, so the gene-side chain
+            # (transposed copy, coefficients, tensor-core pass, finish) runs on a second stream and its short
+            # kernels fill the wave tails of the image-side pass.  Both streams start behind everything issued so
+            # far and the caller's stream continues behind both.
+            cur = torch.cuda.current_stream(img_l.device)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                d_txt = grad_text()
+                join = torch.cuda.Event()
+                join.record(side)
+            d_img = grad_image()
+            cur.wait_event(join)
+            d_txt.record_stream(cur)
+        else:
+            if need_i:
+                d_img = grad_image()
+            if need_t:
+                d_txt = grad_text()
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)
