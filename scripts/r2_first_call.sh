@@ -39,6 +39,13 @@ except Exception as e:
     print("no json", e); print(open("gpurun_out/r2_bench_tune$t.err").read()[-1500:])
 PY
 done
+echo "=== SCL_AUX_V2=1 (row_finalize with 16-byte loads): parity, then the kernel's time in the launch list"
+SCL_AUX_V2=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
+    -k "row_statistics or modules_match or mid_size or wide" > gpurun_out/r2_auxv2_tests.log 2>&1
+echo "exit $?"; tail -2 gpurun_out/r2_auxv2_tests.log
+SCL_AUX_V2=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:row_finalize -c 8 --csv \
+    --log-file gpurun_out/r2_auxv2_launches.csv python bench.py --steps 2 --warmup 1 > /dev/null 2>&1
+grep row_finalize gpurun_out/r2_auxv2_launches.csv | tail -4 | cut -c1-200
 echo "=== SCL_BWD_STREAMS=1 (gene-side backward chain on a second stream): parity, then speed with the one-call-per-phase route timed"
 SCL_BWD_STREAMS=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
     -k "modules_match or bf16_inputs or mid_size or full_size or multi_rank" > gpurun_out/r2_streams_tests.log 2>&1

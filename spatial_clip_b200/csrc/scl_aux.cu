@@ -338,9 +338,103 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restr
   }
   if (lane == 0) row_stats[row] = make_float4(m + log2f(s0), mu, var, zq);
 }
+// Developer variant (SCL_AUX_V2=1; the kernel above measured 24 % of the copy bandwidth, profiles/r1_hbm_passes.md,
+// because every dot product walks its two 1 KB rows in eight dependent 4-byte steps per lane): the same contract
+// with 16-byte loads, all loads of a dot product in flight together and the slot list of the row read once.
+// Summation order inside a dot product differs from the kernel above (last-bit differences in zq).
+__device__ __forceinline__ float dot8(const uint4& ua, const uint4& ub, float acc) {
+  const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
+  const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wa[k]));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wb[k]));
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+  return acc;
+}
+__global__ void __launch_bounds__(256) row_finalize_v2_kernel(const float4* __restrict__ partial, int n_slots,
+                                                              int m_pad, int m_rows, int d,
+                                                              const __nv_bfloat16* __restrict__ x_rows,
+                                                              const __nv_bfloat16* __restrict__ y_all,
+                                                              const int* __restrict__ pos_col,
+                                                              const float* __restrict__ pos_q, int kp1,
+                                                              float4* __restrict__ row_stats) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= m_rows) return;
+  // this row's slots: lane t holds slot t (kp1 <= 32 on this path)
+  int my_col = -1;
+  float my_q = 0.f;
+  if (lane < kp1) {
+    my_col = pos_col[static_cast<size_t>(row) * kp1 + lane];
+    my_q = pos_q[static_cast<size_t>(row) * kp1 + lane];
+  }
+  float m = -INFINITY;
+  for (int s = lane; s < n_slots; s += 32) m = fmaxf(m, partial[static_cast<size_t>(s) * m_pad + row].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int s = lane; s < n_slots; s += 32) {
+    const float4 p = partial[static_cast<size_t>(s) * m_pad + row];
+    const float w = (p.x == -INFINITY) ? 0.f : exp2f(p.x - m);
+    s0 = fmaf(p.y, w, s0);
+    s1 = fmaf(p.z, w, s1);
+    s2 = fmaf(p.w, w, s2);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float mu = s1 / s0;
+  const float var = s2 / s0 - mu * mu;
+  const __nv_bfloat16* xr = x_rows + static_cast<size_t>(row) * d;
+  float zq = 0.f;
+  for (int t = 0; t < kp1; ++t) {
+    const int c = __shfl_sync(0xffffffffu, my_col, t);
+    if (c < 0) continue;  // warp-uniform
+    const float q = __shfl_sync(0xffffffffu, my_q, t);
+    const __nv_bfloat16* yr = y_all + static_cast<size_t>(c) * d;
+    float acc = 0.f;
+    int cb = lane * 8;
+    for (; cb + 768 < d; cb += 1024) {  // four 16-byte pairs in flight per lane
+      const uint4 a0 = *reinterpret_cast<const uint4*>(xr + cb), b0 = *reinterpret_cast<const uint4*>(yr + cb);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(xr + cb + 256), b1 = *reinterpret_cast<const uint4*>(yr + cb + 256);
+      const uint4 a2 = *reinterpret_cast<const uint4*>(xr + cb + 512), b2 = *reinterpret_cast<const uint4*>(yr + cb + 512);
+      const uint4 a3 = *reinterpret_cast<const uint4*>(xr + cb + 768), b3 = *reinterpret_cast<const uint4*>(yr + cb + 768);
+      acc = dot8(a3, b3, dot8(a2, b2, dot8(a1, b1, dot8(a0, b0, acc))));
+    }
+    for (; cb + 256 < d; cb += 512) {  // two pairs
+      const uint4 a0 = *reinterpret_cast<const uint4*>(xr + cb), b0 = *reinterpret_cast<const uint4*>(yr + cb);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(xr + cb + 256), b1 = *reinterpret_cast<const uint4*>(yr + cb + 256);
+      acc = dot8(a1, b1, dot8(a0, b0, acc));
+    }
+    for (; cb < d; cb += 256) {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(xr + cb), b0 = *reinterpret_cast<const uint4*>(yr + cb);
+      acc = dot8(a0, b0, acc);
+    }
+    zq = fmaf(q, warp_sum(acc), zq);
+  }
+  if (lane == 0) row_stats[row] = make_float4(m + log2f(s0), mu, var, zq);
+}
+static bool aux_v2() {
+  static const bool on = [] {
+    const char* e = std::getenv("SCL_AUX_V2");
+    return e != nullptr && e[0] == '1' && e[1] == 0;
+  }();
+  return on;
+}
+
 cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, int m_rows, int d, const void* x_rows,
                                 const void* y_all, const int32_t* pos_col, const float* pos_q, int kp1,
                                 float4* row_stats, cudaStream_t stream) {
+  if (aux_v2() && kp1 <= 32 && d % 8 == 0) {
+    row_finalize_v2_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(partial, n_slots, m_pad, m_rows, d,
+                                                                 static_cast<const __nv_bfloat16*>(x_rows),
+                                                                 static_cast<const __nv_bfloat16*>(y_all), pos_col,
+                                                                 pos_q, kp1, row_stats);
+    return cudaGetLastError();
+  }
   row_finalize_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(partial, n_slots, m_pad, m_rows, d,
                                                             static_cast<const __nv_bfloat16*>(x_rows),
                                                             static_cast<const __nv_bfloat16*>(y_all), pos_col, pos_q,
