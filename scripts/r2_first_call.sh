@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-2 first GPU call (1 GPU, ~12 min): parity of the default kernels, then the opt-in SCL_BWD_TUNE
+# Round-2 first GPU call (1 GPU, ~30-35 min; every === block is independent): parity of the default kernels, then the opt-in SCL_BWD_TUNE
 # instantiations (parity first, then speed), then the per-role wait-cycle counters -- everything lands in gpurun_out/.
-#   gpurun --timeout 1200 -- 'bash scripts/r2_first_call.sh'
+#   gpurun --timeout 2700 -- 'bash scripts/r2_first_call.sh'
 mkdir -p gpurun_out
 echo "=== default parity"; timeout 400 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/r2_gpu_tests.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2_gpu_tests.log
 for t in 1 2 3 7; do
