@@ -79,7 +79,38 @@ probe(int rounds, int both_ways, long long* out) {
   cluster_sync_all();
 }
 
+// how many clusters of `csize` CTAs (608 threads, 227 KB dynamic smem each: the pair kernels' footprint) fit at once
+__global__ void __launch_bounds__(608, 1) footprint_kernel(int* p) {
+  extern __shared__ uint8_t s[];
+  if (p != nullptr && threadIdx.x == 0) p[blockIdx.x] = s[0];
+}
+static int max_clusters(int csize) {
+  const int smem_bytes = 231424;
+  cudaFuncSetAttribute(footprint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(footprint_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * 64);
+  cfg.blockDim = dim3(608);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = csize;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, footprint_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
 int main() {
+  for (int cs : {1, 2, 4, 8})
+    printf("co-resident clusters of %d CTAs (608 threads, 226 KB smem each): %d  -> %d SMs busy\n", cs, max_clusters(cs),
+           cs * max_clusters(cs));
   const int rounds = 64, smem = 2 * kTile + 2048;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long* out;
