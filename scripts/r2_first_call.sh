@@ -80,5 +80,8 @@ echo "exit $?"; grep -E "passed|failed" gpurun_out/r2_shapes_tests.log | tail -2
 echo "=== DSMEM hand-over probe (feasibility of the split-role backward)"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I spatial_clip_b200/csrc tools/dsmem_probe.cu -o /tmp/dsmem_probe 2>/dev/null || cp tools/dsmem_probe.bin /tmp/dsmem_probe
 timeout 60 /tmp/dsmem_probe > gpurun_out/r2_dsmem_probe.txt 2>&1; cat gpurun_out/r2_dsmem_probe.txt
+echo "=== may tcgen05.mma consume an operand another SM stored with st.shared::cluster, and with which fences?"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I spatial_clip_b200/csrc tools/dsmem_mma_probe.cu -o /tmp/dsmem_mma_probe 2>/dev/null || cp tools/dsmem_mma_probe.bin /tmp/dsmem_mma_probe
+timeout 120 /tmp/dsmem_mma_probe > gpurun_out/r2_dsmem_mma_probe.txt 2>&1; cat gpurun_out/r2_dsmem_mma_probe.txt
 echo "=== wait-cycle counters (default kernels)"
 timeout 300 python tools/kernel_timing.py > gpurun_out/r2_kernel_timing.txt 2>&1; tail -40 gpurun_out/r2_kernel_timing.txt

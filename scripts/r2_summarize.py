@@ -96,7 +96,7 @@ if multi:
     print("== bench, several GPUs (--kernel-events after)")
     for p in multi:
         print(bench_row(p.stem[len("r2_bench_"):], bench(p)))
-for name in ("r2_dsmem_probe.txt", "r2_kernel_timing.txt"):
+for name in ("r2_dsmem_probe.txt", "r2_dsmem_mma_probe.txt", "r2_kernel_timing.txt"):
     p = out / name
     if p.exists():
         print(f"== {name}")
