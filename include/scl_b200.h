@@ -180,7 +180,9 @@ typedef struct scl_fwd_args {
   int phases;                                              /* 0 = all; bit 0 soft targets (needs the gathered ids),
                                                               bit 1 image-rows pass (needs txt_all), bit 2 text-rows
                                                               pass + reductions (needs img_all): one call per phase
-                                                              lets the caller overlap the three all-gathers       */
+                                                              lets the caller overlap the three all-gathers;
+                                                              6 (no bit 0): col_* / q_* hold soft targets the
+                                                              caller resolved itself (data-side lists)             */
 } scl_fwd_args;
 size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant);
 int scl_fwd_all(const scl_fwd_args* a, void* stream);
