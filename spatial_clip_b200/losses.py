@@ -346,6 +346,14 @@ class _LossBase(nn.Module):
         if logit_bias is not None and torch.as_tensor(logit_bias).numel() != 1:
             raise NotImplementedError("only a scalar logit_bias is supported (it cancels in both softmaxes)")
 
+    _KERNEL_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
+
+    @classmethod
+    def _kernel_dtype(cls, t: torch.Tensor) -> torch.Tensor:
+        """The kernels read fp32 / bf16 / fp16 features; anything else (e.g. float64, which the reference's torch ops
+        would accept) goes through an autograd-tracked cast to fp32, so its gradient comes back in the caller's dtype."""
+        return t if t.dtype in cls._KERNEL_DTYPES else t.to(torch.float32)
+
     @staticmethod
     def _scale_tensor(logit_scale, like):
         if not torch.is_tensor(logit_scale):
@@ -373,6 +381,7 @@ class SpatialLoss(_LossBase):
                 neighbor_alphas: torch.Tensor, logit_bias: Optional[torch.Tensor] = None,
                 output_dict: bool = True) -> Dict[str, torch.Tensor]:
         self._check_features(image_features, text_features, logit_bias)
+        image_features, text_features = self._kernel_dtype(image_features), self._kernel_dtype(text_features)
         b = image_features.shape[0]
         if neighbor_tile_ids.dim() != 2 or neighbor_tile_ids.shape[0] != b or \
                 neighbor_alphas.shape != neighbor_tile_ids.shape or image_tile_ids.shape[0] != b or \
@@ -408,6 +417,7 @@ class SpatialLossFromColumns(SpatialLoss):
                 positive_probs_text: Optional[torch.Tensor] = None, logit_bias: Optional[torch.Tensor] = None,
                 output_dict: bool = True) -> Dict[str, torch.Tensor]:
         self._check_features(image_features, text_features, logit_bias)
+        image_features, text_features = self._kernel_dtype(image_features), self._kernel_dtype(text_features)
         b = image_features.shape[0]
         if positive_columns.dim() != 2 or positive_columns.shape[0] != b or \
                 positive_probs.shape != positive_columns.shape:
@@ -451,6 +461,7 @@ class ClipLoss(_LossBase):
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
                 logit_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self._check_features(image_features, text_features, logit_bias)
+        image_features, text_features = self._kernel_dtype(image_features), self._kernel_dtype(text_features)
         cfg = _Cfg("clip", self.rank, self.world_size, self.local_loss, self.gather_with_grad, None, 0.0, 1.0,
                    self.process_group, self.precision == "fp32", self.track_retrieval_ranks)
         loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,

@@ -287,3 +287,18 @@ def test_retrieval_ranks_reproduce_reference_recall(n, k_nbr, emulated):
     plain = ClipLoss()
     plain(b.image_features, txt, torch.tensor(20.0))
     assert plain.last_retrieval_ranks is None
+
+
+def test_float64_features_are_accepted_like_the_reference(emulated):
+    """The reference's torch ops take any float dtype; the kernels read fp32 / bf16 / fp16.  Other dtypes go through an
+    autograd-tracked cast, and the gradients come back in the caller's dtype."""
+    meta, gold = load_golden("spatial_n64_k8_default")
+    b = make_spot_batch(**meta["gen"])
+    img = b.image_features.double().requires_grad_(True)
+    txt = b.text_features.double().requires_grad_(True)
+    s = torch.tensor(float(meta["scale"]), requires_grad=True)
+    out = _build(meta)(img, txt, s, b.tile_ids, b.tile_ids, b.neighbor_tile_ids, b.neighbor_alphas)
+    out["contrastive_loss"].backward()
+    assert img.grad.dtype == torch.float64 and txt.grad.dtype == torch.float64
+    _assert_close(gold, 0, meta["gen"]["n"], float(out["contrastive_loss"].detach()), img.grad.float().numpy(),
+                  txt.grad.float().numpy(), float(s.grad), meta["scale"])
