@@ -212,6 +212,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ctx.c = c
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
         ctx.scale_shape = logit_scale.shape
+        ctx.scale_device = logit_scale.device
         ctx.transposed = (img_t, txt_t)  # None unless produced above
         ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
                               q_ti)
@@ -293,7 +294,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
                 d_txt = grad_text()
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
-            d_scale = (go * out4[2]).to(ctx.in_dtypes[2]).reshape(ctx.scale_shape)
+            d_scale = (go * out4[2]).to(device=ctx.scale_device, dtype=ctx.in_dtypes[2]).reshape(ctx.scale_shape)
         return d_img, d_txt, d_scale, None, None, None, None, None, None
 
 
