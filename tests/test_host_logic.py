@@ -302,3 +302,41 @@ def test_float64_features_are_accepted_like_the_reference(emulated):
     assert img.grad.dtype == torch.float64 and txt.grad.dtype == torch.float64
     _assert_close(gold, 0, meta["gen"]["n"], float(out["contrastive_loss"].detach()), img.grad.float().numpy(),
                   txt.grad.float().numpy(), float(s.grad), meta["scale"])
+
+
+@pytest.mark.parametrize("kind", ["spatial", "clip", "columns"])
+def test_lightning_module_dispatch_by_parameter_name(kind, emulated):
+    """What SpatialClipLitModule does with its loss_fn (spatial_clip_module.py:44,50-67), restated: cache the forward's
+    parameter names, merge the net's outputs with the collated batch, pass only the keys the loss names, read
+    "contrastive_loss".  The net emits logit_bias=None (spatial_clip_net.py:52); images / texts / raw_text stay out."""
+    from spatial_clip_b200 import SpatialLossFromColumns
+    from spatial_clip_b200.positives import collate_positive_columns
+
+    b = make_spot_batch(n=24, d=64, k=6, seed=11)
+    cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+               neighbor_alpha_scale=0.5, float32_logits=True)
+    loss_fn = {"spatial": lambda: SpatialLoss(**cfg), "clip": lambda: ClipLoss(local_loss=True, gather_with_grad=True,
+                                                                                 cache_labels=True),
+               "columns": lambda: SpatialLossFromColumns(**cfg)}[kind]()
+    arg_names = set(inspect.signature(loss_fn.forward).parameters.keys())
+    batch = {"images": torch.zeros(24, 3, 8, 8), "texts": torch.zeros(24, 16, dtype=torch.long),
+             "image_tile_ids": b.tile_ids, "text_tile_ids": b.tile_ids.clone(),
+             "neighbor_tile_ids": b.neighbor_tile_ids, "neighbor_alphas": b.neighbor_alphas, "raw_text": ["x"] * 24}
+    if kind == "columns":  # the collate hook of INTEGRATION.md
+        batch = collate_positive_columns(batch, cfg["neighbor_alpha_scale"])
+    img = b.image_features.clone().requires_grad_(True)
+    txt = b.text_features.clone().requires_grad_(True)
+    s = torch.tensor(14.0, requires_grad=True)
+    features = {"image_features": img, "text_features": txt, "logit_scale": s, "logit_bias": None}
+    available = {**features, **batch}
+    loss_input = {k: v for k, v in available.items() if k in arg_names}
+    assert "images" not in loss_input and "raw_text" not in loss_input and "logit_bias" in loss_input
+    out = loss_fn(**loss_input)
+    loss = out["contrastive_loss"]
+    assert loss.dim() == 0 and loss.requires_grad
+    loss.backward()
+    assert img.grad is not None and txt.grad is not None and s.grad is not None
+    if kind == "columns":  # same numbers as the id route
+        ref = SpatialLoss(**cfg)(b.image_features, b.text_features, torch.tensor(14.0), b.tile_ids, b.tile_ids,
+                                 b.neighbor_tile_ids, b.neighbor_alphas)["contrastive_loss"]
+        np.testing.assert_allclose(float(loss.detach()), float(ref), rtol=1e-6)
