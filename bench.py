@@ -91,6 +91,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons polled through NVML every ~2 ms while the timed region runs.  The timed region of
+    the default run lasts ~60 ms, which nvidia-smi's 200 ms loop (ClockSampler, the fallback) barely sees."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def __init__(self, torch_device, period_s=0.002):
+        self.dev = torch_device
+        self.period = period_s
+        self.sm, self.power, self.mask = [], [], 0
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._handle = None
+
+    def start(self) -> bool:
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                idx = self.dev.index or 0
+                if ids and all(v.isdigit() for v in ids) and idx < len(ids):
+                    idx = int(ids[idx])
+                handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)  # must work before the thread relies on it
+            self._nvml, self._handle = pynvml, handle
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+            return True
+        except Exception:
+            return False
+
+    def _run(self):
+        nv, h = self._nvml, self._handle
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        return self.summary(self.sm, self.sm_max, self.mask, self.power, self.period)
+
+    @classmethod
+    def summary(cls, sm, sm_max, mask, power, period):
+        sm = sorted(sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": sm_max,
+                "reasons": [name for bit, name in cls.REASONS if mask & bit], "samples": len(sm),
+                "power_w_max": max(power) if power else None, "source": f"nvml, {period * 1e3:.0f} ms period"}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's torch port of the reference on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -200,8 +267,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         step({k: v.detach() for k, v in dev_in.items()})
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = NvmlSampler(dev)
+    if rank == 0 and not sampler.start():  # no NVML binding / handle: nvidia-smi loop instead
+        sampler = ClockSampler(local_rank)
         sampler.start()
     # roofline of the dominant kernel: CUDA events around its launches, by default inside the timed steps themselves
     # (the backward then goes out as three host calls per direction); --kernel-events after records them in two extra
