@@ -394,7 +394,7 @@ class SpatialLoss(_LossBase):
         loss, col, w, q, ranks = _ContrastiveLossFn.apply(image_features, text_features,
                                                           self._scale_tensor(logit_scale, image_features),
                                                           image_tile_ids, text_tile_ids, neighbor_tile_ids,
-                                                          neighbor_alphas, cfg)
+                                                          neighbor_alphas, cfg, None)
         self.last_positives = (col, w, q)
         self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
         return {"contrastive_loss": loss}
@@ -467,7 +467,7 @@ class ClipLoss(_LossBase):
                    self.process_group, self.precision == "fp32", self.track_retrieval_ranks)
         loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,
                                                         self._scale_tensor(logit_scale, image_features), None, None,
-                                                        None, None, cfg)
+                                                        None, None, cfg, None)
         self.last_retrieval_ranks = ranks if self.track_retrieval_ranks else None
         return {"contrastive_loss": loss}
 
