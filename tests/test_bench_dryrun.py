@@ -1,0 +1,103 @@
+"""Dry run of bench.py's own control flow on the CPU: the CUDA runtime objects it touches (streams, events, pinned
+memory, the device) are replaced by inert stand-ins and the compute backend by the TEST-ONLY emulated ops, at a
+tiny problem size.  Nothing is measured -- the point is that every line of the timed loop, the end-to-end loop (both
+read-back modes), the kernel-event modes and the JSON assembly executes without a GPU, so that a typo cannot cost the
+round its bench line.  Runs in a subprocess because it patches torch globally."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+HARNESS = r'''
+import json, sys, types
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import torch
+import bench
+from emulated_ops import EmulatedOps
+from spatial_clip_b200 import losses
+
+real_device = torch.device
+class FakeEvent:
+    def __init__(self, enable_timing=False): pass
+    def record(self, stream=None): pass
+    def elapsed_time(self, other): return 1.0
+    def synchronize(self): pass
+class FakeStream:
+    def __init__(self, device=None): self.cuda_stream = 0
+    def wait_event(self, ev): pass
+class FakeCtx:
+    def __init__(self, s): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+torch.device = lambda *a, **k: real_device("cpu")
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+torch.cuda.current_stream = lambda *a, **k: FakeStream()
+torch.cuda.Stream = FakeStream
+torch.cuda.Event = FakeEvent
+torch.cuda.stream = FakeCtx
+torch.Tensor.pin_memory = lambda self: self
+torch.Tensor.record_stream = lambda self, s: None
+
+class Ops(EmulatedOps):
+    launches = 0
+    kernel_events = None
+    def fwd_plan(self, m, n, d): return types.SimpleNamespace(variant=1)
+    def split_cast(self, x, want_rows=True, want_cols=True): return x.clone(), x.clone()
+    def bwd_rows(self, *a, **k):
+        if self.kernel_events is not None:
+            self.kernel_events.setdefault("bwd_rows", []).append((FakeEvent(), FakeEvent()))
+        k.pop("split", None)
+        return super().bwd_rows(*a, **k)
+    def fwd_rowstats(self, *a, **k):
+        if self.kernel_events is not None:
+            self.kernel_events.setdefault("fwd_rowstats", []).append((FakeEvent(), FakeEvent()))
+        return super().fwd_rowstats(*a, **k)
+losses._set_ops_for_testing(Ops(round_bf16=False))
+bench.N_GLOBAL, bench.D, bench.K = 256, 64, 4
+orig_sample = bench.cpu_reference_sample
+bench.cpu_reference_sample = lambda rows, steps=1, warmup=0: orig_sample(64, steps=1, warmup=0)
+if %(break_deferred)r:  # the deferred read-back raises -> the blocking loop must take over
+    real_copy = torch.Tensor.copy_
+    def bad_copy(self, src, non_blocking=False):
+        if non_blocking and self.dim() == 0: raise RuntimeError("simulated failure of the pinned copy")
+        return real_copy(self, src)
+    torch.Tensor.copy_ = bad_copy
+sys.argv = ["bench.py", "--steps", "3", "--warmup", "1"] + %(extra)r
+bench.main()
+'''
+
+
+def _run(extra, break_deferred=False):
+    code = HARNESS % {"root": str(ROOT), "extra": extra, "break_deferred": break_deferred}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("extra", [[], ["--kernel-events", "after"]])
+def test_bench_control_flow_runs_end_to_end(extra):
+    j = _run(extra)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in j, key
+    assert j["steps"] == 3 and j["n_gpus"] == 1 and j["unit"] == "pairs/s" and j["vs_baseline"] is None
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "pipeline"} <= set(j["e2e"])
+    assert "one step behind" in j["e2e"]["pipeline"] and j["e2e"]["h2d_bytes_per_step"] > 0
+    r = j["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["launches_per_step"] == 2
+    assert r["kernel_events"] == (extra[1] if extra else "step")
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"]) and j["cpu_baseline"]["kind"] == "port"
+    assert j["config"]["workload"] and "model" not in j["config"]
+
+
+def test_bench_falls_back_to_blocking_readback():
+    j = _run([], break_deferred=True)
+    assert "blocking" in j["e2e"]["pipeline"] and "simulated failure" in j["e2e"]["pipeline"]
+    assert j["e2e"]["value"] > 0
