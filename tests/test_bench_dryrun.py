@@ -33,6 +33,9 @@ class FakeCtx:
     def __init__(self, s): pass
     def __enter__(self): return self
     def __exit__(self, *a): return False
+import torch.distributed as dist
+real_init = dist.init_process_group
+dist.init_process_group = lambda backend, **k: real_init("gloo")  # the N > 1 flow over gloo (env:// rendezvous)
 torch.device = lambda *a, **k: real_device("cpu")
 torch.cuda.set_device = lambda *a, **k: None
 torch.cuda.synchronize = lambda *a, **k: None
@@ -67,17 +70,42 @@ if %(break_deferred)r:  # the deferred read-back raises -> the blocking loop mus
         if non_blocking and self.dim() == 0: raise RuntimeError("simulated failure of the pinned copy")
         return real_copy(self, src)
     torch.Tensor.copy_ = bad_copy
-sys.argv = ["bench.py", "--steps", "3", "--warmup", "1"] + %(extra)r
+sys.argv = ["bench.py", "--steps", "3", "--warmup", "1", "--gpus", str(%(world)d)] + %(extra)r
 bench.main()
 '''
 
 
 def _run(extra, break_deferred=False):
-    code = HARNESS % {"root": str(ROOT), "extra": extra, "break_deferred": break_deferred}
+    code = HARNESS % {"root": str(ROOT), "extra": extra, "break_deferred": break_deferred, "world": 1}
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def _run_world(extra, world=2):
+    """The torchrun flow: one process per rank with RANK / WORLD_SIZE / MASTER_* in the environment."""
+    import os
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    code = HARNESS % {"root": str(ROOT), "extra": extra, "break_deferred": False, "world": world}
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                      text=True, env=env))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (_, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-3000:]
+    lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, outs[0][0][-2000:]
+    for out, _ in outs[1:]:  # only rank 0 prints
+        assert not [ln for ln in out.splitlines() if ln.startswith("{")]
     return json.loads(lines[0])
 
 
@@ -101,3 +129,12 @@ def test_bench_falls_back_to_blocking_readback():
     j = _run([], break_deferred=True)
     assert "blocking" in j["e2e"]["pipeline"] and "simulated failure" in j["e2e"]["pipeline"]
     assert j["e2e"]["value"] > 0
+
+
+@pytest.mark.parametrize("extra", [[], ["--kernel-events", "after"]])
+def test_bench_control_flow_two_ranks(extra):
+    """N > 1: process group, barriers, max-over-ranks reductions, every rank in the kernel-event steps, rank 0 alone
+    in the tail (forward-kernel timing, CPU baseline, the JSON line) while the other ranks leave."""
+    j = _run_world(extra, 2)
+    assert j["n_gpus"] == 2 and j["config"]["local_batch"] == 128 and j["scaling"] == "strong"
+    assert j["roofline"]["launches_per_step"] == 2 and j["e2e"]["value"] > 0
