@@ -138,3 +138,25 @@ def test_bench_control_flow_two_ranks(extra):
     j = _run_world(extra, 2)
     assert j["n_gpus"] == 2 and j["config"]["local_batch"] == 128 and j["scaling"] == "strong"
     assert j["roofline"]["launches_per_step"] == 2 and j["e2e"]["value"] > 0
+
+
+def test_graft_entry_smoke_control_flow():
+    """__graft_entry__.smoke() with the same stand-ins: build(), the module call, the oracle comparison."""
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+import torch
+from emulated_ops import EmulatedOps
+from spatial_clip_b200 import losses
+real_device = torch.device
+torch.device = lambda *a, **k: real_device("cpu")
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+losses._set_ops_for_testing(EmulatedOps(round_bf16=True))
+import __graft_entry__ as g
+g.smoke()
+''' % (str(ROOT), str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "smoke ok" in r.stdout
