@@ -54,10 +54,11 @@ class EmulatedOps:
             return col, w, q
         rows, sums = soft_label_triples(all_ids.numpy(), nbr_ids.numpy(), nbr_alpha.numpy(), alpha_scale, rank)
         for i, lst in enumerate(rows):
+            inv = np.float32(1.0) / max(np.float32(sums[i]), np.float32(1e-12))  # the kernel multiplies by 1/sum in fp32
             for t, (c, ww) in enumerate(lst):
                 col[i, t] = c
                 w[i, t] = float(ww)
-                q[i, t] = float(ww) / max(float(sums[i]), 1e-12)
+                q[i, t] = float(np.float32(ww) * inv)
         return col, w, q
 
     def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
