@@ -160,3 +160,32 @@ g.smoke()
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert "smoke ok" in r.stdout
+
+
+def test_nvml_sampler_with_a_stand_in_binding(monkeypatch):
+    """bench.NvmlSampler against a fake pynvml: handle lookup, polling thread, median / reasons / power summary."""
+    import time
+    import types
+
+    sys.path.insert(0, str(ROOT))
+    import torch
+
+    import bench
+
+    clocks = iter([1965, 1750, 1740, 1755, 1620] + [1750] * 10000)
+    fake = types.SimpleNamespace(
+        NVML_CLOCK_SM=1, nvmlInit=lambda: None,
+        nvmlDeviceGetHandleByUUID=lambda u: (_ for _ in ()).throw(RuntimeError("no such uuid")),
+        nvmlDeviceGetHandleByIndex=lambda i: ("handle", i),
+        nvmlDeviceGetMaxClockInfo=lambda h, c: 1965,
+        nvmlDeviceGetClockInfo=lambda h, c: next(clocks),
+        nvmlDeviceGetCurrentClocksThrottleReasons=lambda h: 0x4,
+        nvmlDeviceGetPowerUsage=lambda h: 998000)
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5")
+    s = bench.NvmlSampler(torch.device("cpu"), period_s=0.001)
+    assert s.start() and s._handle == ("handle", 3)  # UUID lookup failed -> index through CUDA_VISIBLE_DEVICES
+    time.sleep(0.05)
+    out = s.stop()
+    assert out["samples"] >= 5 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert out["sm_mhz"] == 1750.0 and out["sm_min_mhz"] == 1620.0 and abs(out["power_w_max"] - 998.0) < 1e-9
