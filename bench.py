@@ -135,13 +135,16 @@ class NvmlSampler:
 
     def _run(self):
         nv, h = self._nvml, self._handle
+        n = 0
         while not self._stop.is_set():
-            try:
+            try:  # two light queries per poll; the power reading (slower) only every 16th
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                if n % 16 == 0:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
             except Exception:
                 pass
+            n += 1
             time.sleep(self.period)
 
     def stop(self):
