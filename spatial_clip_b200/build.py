@@ -27,12 +27,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libscl_b200.so")
 
 
+STAMP = PKG / "libscl_b200.so.sha"  # digest of the sources + flags the .so was built from (travels with the .so)
+
+
+def _source_digest() -> str:
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))) + \
+        [PKG.parent / "include/scl_b200.h"]
+    for p in deps:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """Stale when the library is missing or was built from other sources.  Compared by content, not by mtime: a
+    snapshot copied to another box keeps the bytes but not necessarily the order of the timestamps."""
     if not LIB.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include/scl_b200.h"]
-    return any(p.stat().st_mtime > t for p in deps)
+    if not STAMP.exists():  # library from before the stamp existed: fall back to timestamps
+        t = LIB.stat().st_mtime
+        deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + \
+            [PKG.parent / "include/scl_b200.h"]
+        return any(p.stat().st_mtime > t for p in deps)
+    return STAMP.read_text().strip() != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -58,6 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    STAMP.write_text(_source_digest() + "\n")
     (objdir / "ptxas.log").write_text("\n".join(logs))
     if verbose:
         print("\n".join(logs))
