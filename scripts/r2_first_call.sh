@@ -61,6 +61,9 @@ except Exception as e:
     print("no json", e); print(open("gpurun_out/r2_bench_streams$st.err").read()[-1500:])
 PY
 done
+echo "=== everything at once (TUNE=7, MN, AUX_V2, STREAMS), one-call-per-phase route timed"
+SCL_BWD_TUNE=7 SCL_BWD_MN=1 SCL_AUX_V2=1 SCL_BWD_STREAMS=1 timeout 300 python bench.py --steps 8 --warmup 3 --kernel-events after > gpurun_out/r2_bench_all.json 2> gpurun_out/r2_bench_all.err
+echo "exit $?"; tail -c 400 gpurun_out/r2_bench_all.json | head -c 400; echo
 echo "=== fixture with different image / text tile ids (added after the last B200 run)"
 SCL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k asym > gpurun_out/r2_asym_tests.log 2>&1
 echo "exit $?"; tail -2 gpurun_out/r2_asym_tests.log

@@ -84,6 +84,7 @@ rows = [(f"SCL_BWD_TUNE={t}", f"r2_bench_tune{t}.json") for t in (0, 1, 2, 3, 7)
 rows += [("SCL_BWD_MN=1", "r2_bench_mn0.json"), ("SCL_BWD_MN=1 SCL_BWD_TUNE=3", "r2_bench_mn1.json"),
          ("streams off (--kernel-events after)", "r2_bench_streams0.json"),
          ("SCL_BWD_STREAMS=1 (--kernel-events after)", "r2_bench_streams1.json"),
+         ("TUNE=7 MN AUX_V2 STREAMS (--kernel-events after)", "r2_bench_all.json"),
          ("precision=fp32", "r2_bench_fp32.json")]
 base = None
 for name, f in rows:
