@@ -401,16 +401,16 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
     }
   }
   if (phases & 2) {
-  if (a->ranks_out != nullptr)  // image -> gene retrieval ranks within the local block, counted in the same pass
-    rc = scl_fwd_rowstats_ranks(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i,
-                                a->rank * a->b_local, diag_z, rank_partial, a->ranks_out, stream);
-  else
-    rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
-                          nullptr, stream);
-  if (rc != SCL_OK) return rc;
-  rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1, a->stats_i,
-                        stream);
-  if (rc != SCL_OK) return rc;
+    if (a->ranks_out != nullptr)  // image -> gene retrieval ranks within the local block, counted in the same pass
+      rc = scl_fwd_rowstats_ranks(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i,
+                                  a->rank * a->b_local, diag_z, rank_partial, a->ranks_out, stream);
+    else
+      rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
+                            nullptr, stream);
+    if (rc != SCL_OK) return rc;
+    rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1,
+                          a->stats_i, stream);
+    if (rc != SCL_OK) return rc;
   }
   if (!(phases & 4)) return SCL_OK;
   rc = scl_fwd_rowstats(a->txt_l, a->b_local, a->img_all, a->n_global, a->d, a->scalars3, &p, part_t, nullptr, 0,
