@@ -7,11 +7,14 @@
 One "step" = SpatialLoss forward + backward (grads to image features, gene features, logit_scale) over
 one synthetic global batch (SURVEY.md §8d generator), through the reference-facing module API.
 Prints ONE JSON line on rank 0.  Metric/unit/config follow BASELINE.json; ``value`` is whole-job
-pairs/s with inputs resident in HBM, ``e2e`` the same through the module with pinned host buffers
-(H2D of the step's inputs + D2H of the loss inside the timed region), ``roofline`` is for the dominant
-kernel (bwd_rows) from CUDA events recorded around its launches inside the timed region, and
-``cpu_baseline`` is the oracle's torch port of the reference timed on this box's host cores on a
-bounded sample of the same workload.
+pairs/s with inputs resident in HBM (K steps in one timed region, CUDA events, max over ranks; the per-step median is
+reported next to it), ``e2e`` the same through the module with pinned host buffers (H2D of the step's inputs + D2H of
+the loss inside the timed region; the gradients stay on the device, where the optimiser of a training step consumes
+them), ``roofline`` is for the dominant kernel (bwd_rows) from CUDA events recorded around its launches,
+``parity`` compares this very run's loss / d logit_scale / sampled gradient rows with the blockwise fp64 CPU oracle
+(outside the timed region; every rank's rows, so the N > 1 lines carry parity over NCCL), and ``cpu_baseline`` is the
+reference's own loss module (oracle/_ref, else the oracle's torch port) timed on this box's host cores on a bounded
+sample of the same workload.
 """
 from __future__ import annotations
 
@@ -162,13 +165,21 @@ class NvmlSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle's torch port of the reference on the host cores
+# reference arm / cpu baseline: the reference's own loss module on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(rows: int, steps: int = 1, warmup: int = 0):
-    """Time the reference's per-rank step (oracle/torch_port.py) for `rows` local rows of the N=32768
-    workload (a W = N/rows rank emulation, one rank timed).  Returns (pairs/s, seconds per step, cores)."""
+    """Time the reference's per-rank step for `rows` local rows of the N=32768 workload (one rank of a W = N/rows
+    emulation; a W=1 step at N=32768 needs ~90 GB of dense [N, N] fp32 temporaries).  The step is the reference's own
+    SpatialLoss (oracle/_ref bytecode of src/models/components/losses.py, kind "reference") when oracle/_ref travels
+    with the repo, else the oracle's torch port with the same cost structure (kind "port").
+
+    Every rank of the reference rebuilds its two id -> column dicts over all N ids (losses.py:92-93); a W=1 step would
+    build them once for N rows.  That part is therefore timed separately (t_dict) and charged once per N rows:
+    seconds per pair = (t_step - t_dict) / rows + t_dict / N.  Returns a dict with both the raw rank-step and the
+    W=1-equivalent figures."""
     import torch
 
+    from oracle import ref_loader
     from oracle.torch_port import spatial_rank_step
     from spatial_clip_b200.synth import make_spot_batch
 
@@ -176,36 +187,62 @@ def cpu_reference_sample(rows: int, steps: int = 1, warmup: int = 0):
     torch.set_num_threads(cores)
     b = make_spot_batch(n=N_GLOBAL, d=D, k=K, seed=SEED)
     sl = slice(0, rows)
-    times = []
+    world = max(1, N_GLOBAL // rows)
+    use_ref = ref_loader.available() and ref_loader.load_reference() is not None
+    ctor = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=SPATIAL_CFG["cap_logit_scale"],
+                temp_reg_weight=SPATIAL_CFG["temp_reg_weight"], float32_logits=True,
+                neighbor_alpha_scale=SPATIAL_CFG["neighbor_alpha_scale"])
+    times, dict_times = [], []
     for it in range(warmup + steps):
         img_l = b.image_features[sl].clone().requires_grad_(True)
         txt_l = b.text_features[sl].clone().requires_grad_(True)
         s = torch.tensor(SCALE, requires_grad=True)
         t0 = time.perf_counter()
-        spatial_rank_step(img_l, txt_l, b.image_features, b.text_features, s, b.tile_ids, b.neighbor_tile_ids[sl],
-                          b.neighbor_alphas[sl], 0, cap=SPATIAL_CFG["cap_logit_scale"],
-                          temp_reg_weight=SPATIAL_CFG["temp_reg_weight"], alpha_scale=SPATIAL_CFG["neighbor_alpha_scale"])
+        if use_ref:
+            ref_loader.reference_rank_step(img_l, txt_l, b.image_features, b.text_features, s, b.tile_ids,
+                                           b.tile_ids[sl], b.neighbor_tile_ids[sl], b.neighbor_alphas[sl], 0, world,
+                                           ctor)
+        else:
+            spatial_rank_step(img_l, txt_l, b.image_features, b.text_features, s, b.tile_ids, b.neighbor_tile_ids[sl],
+                              b.neighbor_alphas[sl], 0, cap=ctor["cap_logit_scale"],
+                              temp_reg_weight=ctor["temp_reg_weight"], alpha_scale=ctor["neighbor_alpha_scale"])
         dt = time.perf_counter() - t0
+        t1 = time.perf_counter()  # the two dict comprehensions of losses.py:92-93, alone
+        _a = {tid.item(): i for i, tid in enumerate(b.tile_ids)}
+        _b = {tid.item(): i for i, tid in enumerate(b.tile_ids)}
+        dd = time.perf_counter() - t1
         if it >= warmup:
             times.append(dt)
+            dict_times.append(dd)
     sec = sum(times) / len(times)
-    return rows / sec, sec, cores
+    t_dict = min(sum(dict_times) / len(dict_times), 0.9 * sec)
+    sec_per_pair = (sec - t_dict) / rows + t_dict / N_GLOBAL
+    return {"pairs_per_s": 1.0 / sec_per_pair, "rank_step_s": sec, "dict_s": t_dict, "rank_step_pairs_per_s": rows / sec,
+            "cores": cores, "kind": "reference" if use_ref else "port", "rows": rows, "world": world, "steps": len(times)}
+
+
+def cpu_sample_text(r):
+    what = ("the reference's own SpatialLoss (oracle/_ref bytecode of src/models/components/losses.py)"
+            if r["kind"] == "reference" else "oracle/torch_port.py (torch port of the reference)")
+    return (f"{r['rows']} local rows x N={N_GLOBAL} columns (one rank of a W={r['world']} single-process emulation of the "
+            f"same workload), fwd+bwd, {what}, torch CPU fp32, {r['cores']} threads, mean of {r['steps']} rank-steps of "
+            f"{r['rank_step_s']:.2f} s; the {r['dict_s']:.2f} s of per-rank id-dict building is charged once per N rows "
+            f"(W=1 equivalent; the raw rank-step rate is {r['rank_step_pairs_per_s']:.0f} pairs/s)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = 1024
-    pps, sec, cores = cpu_reference_sample(rows, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    sample = (f"{rows} local rows x N={N_GLOBAL} columns (one rank of a W={N_GLOBAL // rows} emulation of the same "
-              f"workload), fwd+bwd, torch CPU fp32, {cores} threads")
+    r = cpu_reference_sample(1024, steps=max(1, min(args.steps, 12)), warmup=min(args.warmup, 1))
+    pps = r["pairs_per_s"]
     line = {
         "impl": "reference", "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
         "value": pps, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {**workload_config(args.gpus), "precision": args.precision},
-        "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": N_GLOBAL / pps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {**workload_config(args.gpus), "precision": args.precision},
+        "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": cpu_sample_text(r)},
         "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -216,14 +253,49 @@ def workload_config(n_gpus):
                         "metric's global batch", "global_batch": N_GLOBAL, "embed_dim": D, "k_neighbors": K,
             "local_batch": N_GLOBAL // n_gpus, "logit_scale": SCALE, **SPATIAL_CFG,
             "parallelism": f"dp{n_gpus} (row shards, local_loss feature all-gather over NCCL)",
-            "l2": "inputs (134 MB fp32 + 134 MB grads) exceed the 126 MB L2; additionally a 256 MB buffer is "
-                  "written between timed steps"}
+            "tile_ids": "image-side and text-side id vectors are distinct tensors (as the reference's collate makes them)",
+            "l2": "a step streams 134 MB of fp32 inputs, 67 MB of bf16 operand copies and 134 MB of gradients (> the "
+                  "126 MB L2), so consecutive steps do not find their inputs in L2; no explicit flush in either loop"}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+PARITY_ROWS_PER_RANK = 8
+
+
+def parity_block(full, world, loss_ranks, ds_ranks, rows, gi_rows, gt_rows, split):
+    """This run's results against the blockwise fp64 CPU oracle (oracle/blockwise_oracle.py) on the operand values the
+    kernels see (bf16-rounded inputs in the bf16 mode, the fp32 inputs in the fp32-accurate mode).  Rank 0 only,
+    outside every timed region."""
+    import numpy as np
+
+    from oracle.blockwise_oracle import blockwise_oracle
+
+    t0 = time.perf_counter()
+    img, txt = full.image_features, full.text_features
+    if not split:
+        img, txt = img.bfloat16().float(), txt.bfloat16().float()
+    ref = blockwise_oracle(img.numpy(), txt.numpy(), SCALE, full.tile_ids.numpy(), full.tile_ids.numpy(),
+                           full.neighbor_tile_ids.numpy(), full.neighbor_alphas.numpy(), world,
+                           SPATIAL_CFG["cap_logit_scale"], SPATIAL_CFG["temp_reg_weight"],
+                           SPATIAL_CFG["neighbor_alpha_scale"], SPATIAL_CFG["local_loss"],
+                           SPATIAL_CFG["gather_with_grad"], rows)
+    loss_rel = float(np.max(np.abs(np.asarray(loss_ranks) - ref.loss) / np.abs(ref.loss)))
+    ds_rel = float(np.max(np.abs(np.asarray(ds_ranks) - ref.d_scale) / np.abs(ref.d_scale)))
+    gi_rel = float(np.abs(gi_rows - ref.d_image_rows).max() / np.abs(ref.d_image_rows).max())
+    gt_rel = float(np.abs(gt_rows - ref.d_text_rows).max() / np.abs(ref.d_text_rows).max())
+    gates = {"loss_rel": 5e-5 if split else 2e-5, "d_scale_rel": 1e-3, "grad_rel_of_max": 1e-4 if split else 5e-3}
+    ok = loss_rel <= gates["loss_rel"] and ds_rel <= gates["d_scale_rel"] and max(gi_rel, gt_rel) <= gates["grad_rel_of_max"]
+    return {"oracle": "oracle/blockwise_oracle.py (fp64, closed-form gradients, W-rank emulation)", "ranks": world,
+            "loss_rank0": float(loss_ranks[0]), "loss_rank0_oracle": float(ref.loss[0]), "loss_rel_max_over_ranks": loss_rel,
+            "d_scale_rel_max_over_ranks": ds_rel, "sampled_rows": len(rows), "d_image_rows_err_of_max": gi_rel,
+            "d_text_rows_err_of_max": gt_rel, "gates": gates, "ok": bool(ok),
+            "transport": "nccl" if world > 1 else "single rank", "oracle_seconds": time.perf_counter() - t0}
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -243,21 +315,22 @@ def run_ours(args):
     full = make_spot_batch(n=N_GLOBAL, d=D, k=K, seed=SEED)
     loc = full.rank_slice(rank, world)
     b_local = N_GLOBAL // world
+    # image-side and text-side tile ids are separate tensors with equal contents, as the reference's collate builds
+    # them (spatial_datamodule.py:126-127)
     host = dict(img=loc.image_features.pin_memory(), txt=loc.text_features.pin_memory(),
-                ids=loc.tile_ids.pin_memory(), nbr=loc.neighbor_tile_ids.pin_memory(),
-                alpha=loc.neighbor_alphas.pin_memory())
+                ids=loc.tile_ids.pin_memory(), tids=loc.tile_ids.clone().pin_memory(),
+                nbr=loc.neighbor_tile_ids.pin_memory(), alpha=loc.neighbor_alphas.pin_memory())
     dev_in = {k: v.to(dev) for k, v in host.items()}
     scale = torch.tensor(SCALE, device=dev, requires_grad=True)
     mod = SpatialLoss(**SPATIAL_CFG, precision=args.precision)
     split = args.precision == "fp32"
     ops = losses._ops()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step(inp):
         img = inp["img"].requires_grad_(True)
         txt = inp["txt"].requires_grad_(True)
         scale.grad = None
-        out = mod(img, txt, scale, inp["ids"], inp["ids"], inp["nbr"], inp["alpha"])["contrastive_loss"]
+        out = mod(img, txt, scale, inp["ids"], inp["tids"], inp["nbr"], inp["alpha"])["contrastive_loss"]
         out.backward()
         return out, img.grad, txt.grad
 
@@ -266,7 +339,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    # ---- device-resident timing: W warm-up steps, then EXACTLY K steps in one timed region
     for _ in range(args.warmup):
         step({k: v.detach() for k, v in dev_in.items()})
     sync_all()
@@ -274,37 +347,45 @@ def run_ours(args):
     if rank == 0 and not sampler.start():  # no NVML binding / handle: nvidia-smi loop instead
         sampler = ClockSampler(local_rank)
         sampler.start()
-    # roofline of the dominant kernel: CUDA events around its launches, by default inside the timed steps themselves
-    # (the backward then goes out as three host calls per direction); --kernel-events after records them in two extra
-    # steps right after the timed loop instead, so that the timed steps use the one-call-per-phase route
-    events_in_step = args.kernel_events == "step"
-    if events_in_step:
-        ops.kernel_events = {}
     launches0 = ops.launches
-    per_step = []
-    for _ in range(args.steps):
-        flush.fill_(1)  # L2 flush, outside the per-step event pair
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        loss, _, _ = step({k: v.detach() for k, v in dev_in.items()})
-        b.record()
-        per_step.append((a, b))
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
+    for i in range(args.steps):
+        loss, g_img, g_txt = step({k: v.detach() for k, v in dev_in.items()})
+        marks[i + 1].record()
     sync_all()
     launches = (ops.launches - launches0) // max(1, args.steps)
-    if not events_in_step:  # every rank takes part: the steps contain the exchanges
-        ops.kernel_events = {}
-        for _ in range(2):
-            flush.fill_(1)
-            step({k: v.detach() for k, v in dev_in.items()})
-        sync_all()
-    kernel_events, ops.kernel_events = ops.kernel_events, None
     clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in per_step) / len(per_step)
-    t = torch.tensor([ms], device=dev)
+    ms = marks[0].elapsed_time(marks[-1]) / args.steps
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    med = per_step[len(per_step) // 2]
+    t = torch.tensor([ms, med], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, med = float(t[0].item()), float(t[1].item())
     loss_val = float(loss.detach())
+
+    # ---- parity inputs: every rank's loss, d logit_scale and a fixed sample of its gradient rows (last timed step)
+    from oracle.blockwise_oracle import sample_rows_for
+
+    rows_all = sample_rows_for(N_GLOBAL, world, PARITY_ROWS_PER_RANK, seed=SEED)
+    my_rows = torch.tensor([r - rank * b_local for r in rows_all if rank * b_local <= r < (rank + 1) * b_local], device=dev)
+    mine = torch.cat([torch.stack([loss.detach().float().reshape(()), scale.grad.detach().float().reshape(())]),
+                      g_img[my_rows].float().reshape(-1), g_txt[my_rows].float().reshape(-1)])
+    if world > 1:
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+    else:
+        allv = [mine]
+    allv = [v.cpu().double().numpy() for v in allv]
+
+    # ---- dominant-kernel timing: two extra steps with CUDA events around the tensor-core launches (the backward then
+    # goes out as three host calls per direction instead of one; the timed steps above use the one-call route)
+    ops.kernel_events = {}
+    for _ in range(2):
+        step({k: v.detach() for k, v in dev_in.items()})
+    sync_all()
+    kernel_events, ops.kernel_events = ops.kernel_events, None
 
     # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> loss D2H, every step.
     # Double-buffered input pipeline: step i+1's H2D copy is enqueued on a copy stream before step i's loss is
@@ -353,7 +434,7 @@ def run_ours(args):
             last = float(loss_host[pending[0]])
         return last
 
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
 
     def time_e2e(deferred):
         e2e_loop(min(2, max(1, args.warmup)), deferred)
@@ -367,10 +448,10 @@ def run_ours(args):
         return t0.elapsed_time(t1) / e2e_steps
 
     e2e_note = ("double-buffered H2D on a copy stream; every step's loss is copied D2H into pinned memory and read by "
-                "the host one step behind")
+                "the host one step behind; the gradients (2 x B_l x D) stay on the device for the optimiser")
     try:
         e2e_local = time_e2e(True)
-    except Exception as exc:  # fall back to the blocking read-back (the loop measured in profiles/r1_bench_*.json)
+    except Exception as exc:  # fall back to the blocking read-back
         e2e_note = ("double-buffered H2D on a copy stream, loss read back (blocking) every step; deferred read-back "
                     f"failed: {type(exc).__name__}: {exc}")[:400]
         e2e_local = time_e2e(False)
@@ -385,74 +466,76 @@ def run_ours(args):
         return
 
     pk = peaks()
-    traffic = None  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (1 GPU)
-    tp = ROOT / "profiles" / "r1_traffic.json"
-    if tp.exists() and world == 1:
-        tj = json.loads(tp.read_text()).get("bwd_rows_pair_kernel", {})
+    prof = {}
+    tp = ROOT / "profiles" / "r2_traffic.json"  # per-launch numbers of the committed ncu --set full capture (1 GPU)
+    if tp.exists():
+        prof = json.loads(tp.read_text())
+    traffic = None
+    if world == 1 and "bwd_rows_pair_kernel" in prof:
+        tj = prof["bwd_rows_pair_kernel"]
         traffic = tj.get("dram_bytes_read", 0) + tj.get("dram_bytes_write", 0)
     # dominant kernel: bwd_rows, two launches per step (d image, d gene)
     ev = kernel_events.get("bwd_rows", [])
     k_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    fev = kernel_events.get("fwd_rowstats", [])
+    f_ms = sum(a.elapsed_time(b) for a, b in fev) / max(1, len(fev))
     alg_flops_launch = 2.0 * b_local * N_GLOBAL * D  # the dX GEMM; the z recompute is not algorithmic work
     mma_factor = 3.0 if split else 1.0  # fp32-accurate mode: three bf16 products per algorithmic one
     achieved = alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    # forward pass kernel, timed on its own after the step loop (inside the step it is part of one composite call).
-    # RANK 0 ONLY from here on: no collectives below -- the column operand is a local stand-in of the right shape
-    # (kernel time does not depend on the values).
-    if split:
-        xb, yb = ops.split_cast(dev_in["img"])
-    else:
-        xb, _ = ops.cast_bf16(dev_in["img"])
-        yb = xb
-    yb = yb.repeat(world, 1) if world > 1 else yb
-    sc3 = ops.prep_scalars(torch.tensor([SPATIAL_CFG["cap_logit_scale"]], device=dev), None)
-    ops.kernel_events = {}
-    for _ in range(4):
-        flush.fill_(1)
-        ops.fwd_rowstats(xb, yb, sc3)
-    torch.cuda.synchronize()
-    fev = ops.kernel_events.get("fwd_rowstats", [])[1:]
-    ops.kernel_events = None
-    f_ms = sum(a.elapsed_time(b) for a, b in fev) / max(1, len(fev))
     pairs_per_s = N_GLOBAL / (ms * 1e-3)
-    step_alg_tflops = (N_GLOBAL / world) / (ms * 1e-3) * 6.0 * N_GLOBAL * D / 1e12  # per GPU, F_alg = 6 N D / pair
-    cpu_steps = 12  # bounded sample: ~10 s of host work (1 untimed + 12 timed rank-steps)
-    cpu_pps, cpu_sec, cores = cpu_reference_sample(1024, steps=cpu_steps, warmup=1)
+    nd = float(N_GLOBAL) * D
+    per_gpu_pairs = (N_GLOBAL / world) / (ms * 1e-3)
+    step_alg_tflops = per_gpu_pairs * 6.0 * nd / 1e12  # F_alg = 6 N D per pair
+    executed_nd = 12.0 * mma_factor  # two forward passes + two backward passes (recompute + gradient GEMM each)
+
+    # ---- parity of this run (loss / d_scale of every rank, sampled gradient rows), CPU oracle, untimed
+    n_s = PARITY_ROWS_PER_RANK
+    gi = np.concatenate([v[2:2 + n_s * D].reshape(n_s, D) for v in allv])
+    gt = np.concatenate([v[2 + n_s * D:2 + 2 * n_s * D].reshape(n_s, D) for v in allv])
+    try:
+        parity = parity_block(full, world, [v[0] for v in allv], [v[1] for v in allv], rows_all, gi, gt, split)
+    except Exception as exc:  # never lose the bench line to the checker
+        parity = {"ok": None, "error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    cpu = cpu_reference_sample(1024, steps=12, warmup=1)  # bounded sample: ~10 s of host work
 
     line = {
         "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
         "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms, "median_ms_per_step": med, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None,
         "dtype": "bf16x2 (fp32-accurate: bf16 hi/lo operand pairs, fp32 accumulate)" if split else "bf16",
         "data": "synthetic", "config": {**workload_config(world), "precision": args.precision},
         "pairs_per_s_per_gpu": pairs_per_s / world,
         "loss": loss_val,
         "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "pipeline": e2e_note},
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "steps": e2e_steps, "pipeline": e2e_note},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel" if ops.fwd_plan(256, 256, D).variant == 1 else "bwd_rows_kernel", "achieved": achieved, "peak": pk["burst"],
+        "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel", "achieved": achieved, "peak": pk["burst"],
                      "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": traffic,
-                     "peak_source": pk["source"], "launch_ms": k_ms, "launches_per_step": len(ev) // max(1, args.steps if events_in_step else 2),
-                     "kernel_events": args.kernel_events,
+                     "peak_source": pk["source"], "launch_ms": k_ms, "launches_per_step": 2,
+                     "timed": "CUDA events around the launches in two extra steps after the timed loop",
                      "algorithmic_flops_per_launch": alg_flops_launch,
                      "frac_of_sustained": achieved / pk["sustained"],
+                     "executed_tflops": 2.0 * mma_factor * achieved,
                      "fwd_rowstats_launch_ms": f_ms,
-                     "fwd_rowstats_tflops": 2.0 * b_local * N_GLOBAL * D / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
+                     "fwd_rowstats_tflops": 2.0 * mma_factor * b_local * N_GLOBAL * D / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
                      "step_algorithmic_tflops_per_gpu": step_alg_tflops,
                      "step_frac_of_burst": step_alg_tflops / pk["burst"],
-                     # executed MMA work of the step: 2 forward passes (2 B_l N D each) + 2 backward passes (similarity
-                     # recompute + gradient GEMM, 4 B_l N D each) = 12 B_l N D per rank -- SURVEY §8d "tensor_pipe_util"
-                     "step_executed_tflops_per_gpu": 2.0 * mma_factor * step_alg_tflops,
-                     "tensor_pipe_util": 2.0 * mma_factor * step_alg_tflops / pk["burst"],
-                     "tensor_pipe_util_of_sustained": 2.0 * mma_factor * step_alg_tflops / pk["sustained"],
-                     "executed_tflops": 2.0 * mma_factor * alg_flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
+                     # BASELINE.md §3 "tensor_pipe_util": executed MMA flop / t / peak with executed = 8 N D per pair
+                     # (one forward pass + two recompute-and-gradient passes); this build still runs TWO forward
+                     # passes, i.e. executes 12 N D per pair, reported separately
+                     "tensor_pipe_util_8nd": step_alg_tflops * 8.0 / 6.0 / pk["burst"],
+                     "executed_nd_per_pair": executed_nd,
+                     "executed_tflops_per_gpu": step_alg_tflops * executed_nd / 6.0,
+                     "executed_frac_of_burst": step_alg_tflops * executed_nd / 6.0 / pk["burst"],
+                     "ncu_tensor_pipe_active_pct": prof.get("tensor_pipe_active_pct"),
                      "note": "achieved counts the dX GEMM only (algorithmic); the launch also recomputes the similarity "
                              "tile once (executed = 2x)"},
-        "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"1024 local rows x N={N_GLOBAL} columns (one rank of a W=32 emulation), fwd+bwd, "
-                                   f"oracle/torch_port.py (torch CPU fp32), mean of {cpu_steps} rank-steps after 1 "
-                                   f"warm-up, {cpu_sec:.2f} s each"},
+        "parity": parity,
+        "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                         "sample": cpu_sample_text(cpu)},
     }
     print(json.dumps(line))
     if world > 1:
@@ -462,11 +545,9 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)  # 10 warm-up + 50 timed
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--kernel-events", choices=["step", "after"], default="step",
-                    help="where the dominant kernel is timed: inside the timed steps (default) or in two extra steps")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="fp32: the fp32-accurate mode (bf16 hi/lo operand pairs), BASELINE configs[4]'s 'fp32 vs bf16'")
     args = ap.parse_args()

@@ -7,7 +7,6 @@ raises.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 from typing import Optional
 
@@ -19,7 +18,7 @@ _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 class SclPlan(C.Structure):
     _fields_ = [("chunks", C.c_int), ("tiles_per_chunk", C.c_int), ("n_slots", C.c_int), ("m_pad", C.c_int),
-                ("n_pad", C.c_int), ("d_split", C.c_int), ("variant", C.c_int), ("split", C.c_int)]
+                ("n_pad", C.c_int), ("d_split", C.c_int), ("split", C.c_int)]
 
 
 class SclError(RuntimeError):
@@ -31,13 +30,12 @@ _VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
 class PrepareArgs(C.Structure):
     _fields_ = [("image", _VP), ("text", _VP), ("src_dtype", _I), ("logit_scale", _VP), ("cap", _F), ("rows", _I),
-                ("d", _I), ("ld_t", _I), ("image_bf16", _VP), ("text_bf16", _VP), ("image_bf16_t", _VP),
-                ("text_bf16_t", _VP), ("scalars3", _VP)]
+                ("d", _I), ("image_bf16", _VP), ("text_bf16", _VP), ("scalars3", _VP)]
 
 
 class FwdArgs(C.Structure):
     _fields_ = [("img_l", _VP), ("txt_l", _VP), ("img_all", _VP), ("txt_all", _VP), ("b_local", _I), ("n_global", _I),
-                ("d", _I), ("rank", _I), ("variant", _I), ("scalars3", _VP), ("img_ids_all", _VP),
+                ("d", _I), ("rank", _I), ("scalars3", _VP), ("img_ids_all", _VP),
                 ("txt_ids_all", _VP), ("nbr_ids", _VP), ("nbr_alpha", _VP), ("k", _I), ("alpha_scale", _F),
                 ("same_ids", _I), ("c", _F), ("w", _F), ("finalize_scalars", _I), ("col_it", _VP), ("w_it", _VP),
                 ("q_it", _VP), ("col_ti", _VP), ("w_ti", _VP), ("q_ti", _VP), ("stats_i", _VP), ("stats_t", _VP),
@@ -46,8 +44,8 @@ class FwdArgs(C.Structure):
 
 
 class BwdArgs(C.Structure):
-    _fields_ = [("x_rows", _VP), ("y_all", _VP), ("y_all_t", _VP), ("ld_t", _I), ("b_local", _I), ("n_global", _I),
-                ("d", _I), ("rank", _I), ("variant", _I), ("row_stats", _VP), ("col_stats_all", _VP), ("pos_col", _VP),
+    _fields_ = [("x_rows", _VP), ("y_all", _VP), ("b_local", _I), ("n_global", _I),
+                ("d", _I), ("rank", _I), ("row_stats", _VP), ("col_stats_all", _VP), ("pos_col", _VP),
                 ("pos_q", _VP), ("opp_q_local", _VP), ("opp_col_all", _VP), ("opp_q_all", _VP), ("k_plus_1", _I),
                 ("gaps", _VP), ("scalars3", _VP), ("grad_out", _VP), ("c", _F), ("w", _F), ("mult", _F),
                 ("col_mode", _I), ("dx_out", _VP), ("out_dtype", _I), ("workspace", _VP), ("workspace_bytes", _SZ),
@@ -59,20 +57,19 @@ EXPORTS = {
     "scl_abi_version": (C.c_int, []),
     "scl_error_string": (C.c_char_p, [C.c_int]),
     "scl_check_device": (C.c_int, [C.POINTER(C.c_int)]),
-    "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
+    "scl_fwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
     "scl_bwd_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
-    "scl_bwd_plan_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SclPlan)]),
     "scl_split_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "scl_transpose_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "scl_cast_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                C.c_void_p]),
+    "scl_cast_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scl_check_positives": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "scl_prep_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "scl_positives_workspace_bytes": (C.c_size_t, [C.c_int]),
     "scl_build_positives": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                       C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
     "scl_fwd_rowstats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                   C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                                   C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "scl_fwd_rowstats_ranks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                          C.POINTER(SclPlan), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
@@ -83,15 +80,15 @@ EXPORTS = {
     "scl_bwd_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(SclPlan), C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                               C.c_void_p, C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_void_p]),
+    "scl_bwd_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                               C.POINTER(SclPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scl_bwd_finish_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "scl_bwd_finish": (C.c_int, [C.c_void_p, C.POINTER(SclPlan), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
-                                 C.c_void_p, C.c_int, C.c_void_p]),
+                                 C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "scl_prepare": (C.c_int, [C.POINTER(PrepareArgs), C.c_void_p]),
-    "scl_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "scl_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "scl_fwd_all": (C.c_int, [C.POINTER(FwdArgs), C.c_void_p]),
     "scl_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "scl_bwd_dir": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
@@ -116,7 +113,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scl_abi_version() != 6:
+    if lib.scl_abi_version() != 7:
         raise SclError("libscl_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -155,27 +152,8 @@ class CudaOps:
     def __init__(self):
         self.lib = load_library()
         self._checked = set()
-        self.variant = -1  # -1: library default (env SCL_VARIANT), 0: single-CTA kernels, 1: CTA-pair kernels
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
-        # developer knob (read by the library too): the gradient GEMM takes Y itself as an MN-major operand, so no
-        # transposed copies are made or passed (bf16 mode, CTA-pair kernels only; not yet run on a B200)
-        self.mn_major = os.environ.get("SCL_BWD_MN") == "1"
-        # developer knob (host side only): at W > 1 issue the feature / id exchanges without waiting and run the forward
-        # in three phases (scl_fwd_args.phases), each behind the wait of the one operand it reads (losses.py)
-        self.overlap_gather = os.environ.get("SCL_OVERLAP_GATHER") == "1"
-        # developer knob (host side only): the gene-side backward chain runs on a second stream next to the image-side
-        # one (losses.py); not with the per-kernel timing modes, which assume one stream
-        self.two_streams = os.environ.get("SCL_BWD_STREAMS") == "1"
-        self._side_streams = {}
-
-    def _cycles(self, name, plan, like):
-        """Developer timing mode: a zeroed int64 buffer (16 counters per CTA) when self.cycle_buffers is a dict."""
-        if getattr(self, "cycle_buffers", None) is None or plan.variant != 1:
-            return None
-        buf = torch.zeros(16 * 4096 * 8, dtype=torch.int64, device=like.device)
-        self.cycle_buffers.setdefault(name, []).append(buf)
-        return buf
 
     def _timed(self, name, device, fn):
         """Run one C-ABI launch, optionally bracketed by CUDA events on its stream (bench.py roofline)."""
@@ -208,15 +186,6 @@ class CudaOps:
             self._checked.add(idx)
         return torch.cuda.current_stream(t.device).cuda_stream
 
-    def side_stream(self, device):
-        """The second stream of `device` for the two-stream backward, or None when a per-kernel timing mode is on."""
-        if self.kernel_events is not None or getattr(self, "cycle_buffers", None) is not None:
-            return None
-        st = self._side_streams.get(device.index)
-        if st is None:
-            st = self._side_streams[device.index] = torch.cuda.Stream(device=device)
-        return st
-
     @staticmethod
     def empty(shape, dtype, like: torch.Tensor) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=like.device)
@@ -224,12 +193,12 @@ class CudaOps:
     # ---------------------------------------------------------------- plans
     def fwd_plan(self, m_rows: int, n_cols: int, d: int) -> SclPlan:
         p = SclPlan()
-        self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, self.variant, C.byref(p)), "scl_fwd_plan")
+        self._check(self.lib.scl_fwd_plan(m_rows, n_cols, d, C.byref(p)), "scl_fwd_plan")
         return p
 
     def bwd_plan(self, m_rows: int, n_cols: int, d: int, split: bool = False) -> SclPlan:
         p = SclPlan()
-        self._check(self.lib.scl_bwd_plan_ex(m_rows, n_cols, d, self.variant, int(split), C.byref(p)), "scl_bwd_plan")
+        self._check(self.lib.scl_bwd_plan(m_rows, n_cols, d, int(split), C.byref(p)), "scl_bwd_plan")
         return p
 
     def check_shapes(self, b_local: int, n_global: int, d: int, split: bool, need_backward: bool):
@@ -239,19 +208,15 @@ class CudaOps:
             self.bwd_plan(b_local, n_global, d, split)
 
     # ---------------------------------------------------------------- ops
-    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
+    def cast_bf16(self, x, normalize=False):
         st = self._stream(x)
         rows, d = x.shape
-        y = self.empty((rows, d), torch.bfloat16, x) if want_rows else None
-        y_t = None
-        if want_t:
-            y_t = torch.zeros((d, ld_t), dtype=torch.bfloat16, device=x.device) if ld_t != rows else \
-                self.empty((d, ld_t), torch.bfloat16, x)
+        y = self.empty((rows, d), torch.bfloat16, x)
         with _DeviceGuard(x.device):
-            self._check(self.lib.scl_cast_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(y), _ptr(y_t), rows, d, ld_t,
-                                               int(normalize), st), "scl_cast_bf16")
+            self._check(self.lib.scl_cast_bf16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(y), rows, d, int(normalize), st),
+                        "scl_cast_bf16")
         self.launches += 1
-        return y, y_t
+        return y
 
     def split_cast(self, x, want_rows=True, want_cols=True):
         """fp32-accurate mode operands: x [rows, D] -> (h|h|l) and/or (h|l|h) bf16 rows of width 3 D (scl_split_bf16)."""
@@ -264,17 +229,6 @@ class CudaOps:
                         "scl_split_bf16")
         self.launches += 1
         return r, c
-
-    def transpose_split(self, cols_all, d, ld_t):
-        """[N, 3 D] = (h|l|h) -> stacked transposed copy [2 D, ld_t] = [h^T ; l^T] (scl_transpose_split)."""
-        st = self._stream(cols_all)
-        n = cols_all.shape[0]
-        new_t = torch.zeros if ld_t != n else torch.empty
-        out = new_t((2 * d, ld_t), dtype=torch.bfloat16, device=cols_all.device)
-        with _DeviceGuard(cols_all.device):
-            self._check(self.lib.scl_transpose_split(_ptr(cols_all), n, d, ld_t, _ptr(out), st), "scl_transpose_split")
-        self.launches += 1
-        return out
 
     def prep_scalars(self, logit_scale, cap):
         st = self._stream(logit_scale)
@@ -305,6 +259,21 @@ class CudaOps:
         self.launches += 3 if k > 0 else 1
         return col, w, q
 
+    def check_positives(self, col, q, n_global, rank):
+        """Sanitised copies of caller-resolved soft-target lists + a device flag (int32[1]) of what was wrong with
+        them (scl_check_positives; bit 0 column out of range, bit 1 slot 0 is not the own column, bit 2 weight on an
+        unused slot)."""
+        st = self._stream(col)
+        b_local, kp1 = col.shape
+        col_out = torch.empty_like(col)
+        q_out = torch.empty_like(q)
+        flag = torch.zeros((1,), dtype=torch.int32, device=col.device)
+        with _DeviceGuard(col.device):
+            self._check(self.lib.scl_check_positives(_ptr(col), _ptr(q), b_local, kp1, n_global, rank, _ptr(col_out),
+                                                     _ptr(q_out), _ptr(flag), st), "scl_check_positives")
+        self.launches += 1
+        return col_out, q_out, flag
+
     def fwd_rowstats(self, x_rows, y_cols, scalars, debug_z=False):
         st = self._stream(x_rows)
         m, d = x_rows.shape
@@ -314,8 +283,7 @@ class CudaOps:
         dbg = torch.zeros((m, n), dtype=torch.float32, device=x_rows.device) if debug_z else None
         with _DeviceGuard(x_rows.device):
             self._check(self._timed("fwd_rowstats", x_rows.device, lambda: self.lib.scl_fwd_rowstats(
-                _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n,
-                _ptr(self._cycles("fwd", plan, x_rows)), st)),
+                _ptr(x_rows), m, _ptr(y_cols), n, d, _ptr(scalars), C.byref(plan), _ptr(partial), _ptr(dbg), n, st)),
                 "scl_fwd_rowstats")
         self.launches += 1
         return (partial, plan, dbg) if debug_z else (partial, plan)
@@ -350,30 +318,26 @@ class CudaOps:
         return out
 
     # ---------------------------------------------------------------- composite phases (one host call each)
-    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t, split=False):
-        """cap + bf16 casts (+ transposed copies) of both modalities: scl_prepare.  Returns the row operands, the
-        column operands (the same tensors unless split), the transposed copies (or None) and the scalars."""
+    def prepare(self, image, text, logit_scale, cap, split=False):
+        """cap + bf16 casts of both modalities, one launch: scl_prepare.  Returns the row operands, the column
+        operands (the same tensors unless split) and the scalars."""
         st = self._stream(image)
         rows, d = image.shape
         if text.dtype != image.dtype:
             text = text.to(image.dtype)
-        if split:  # fp32-accurate mode: bf16 hi/lo pairs, K-concatenated (transposed copies are made in backward)
+        if split:  # fp32-accurate mode: bf16 hi/lo pairs, K-concatenated
             img_r, img_c = self.split_cast(image)
             txt_r, txt_c = self.split_cast(text)
-            return img_r, txt_r, img_c, txt_c, None, None, self.prep_scalars(logit_scale, cap)
-        img = self.empty((rows, d), torch.bfloat16, image)
-        txt = self.empty((rows, d), torch.bfloat16, image)
-        new_t = torch.zeros if ld_t != rows else torch.empty
-        img_t = new_t((d, ld_t), dtype=torch.bfloat16, device=image.device) if want_img_t else None
-        txt_t = new_t((d, ld_t), dtype=torch.bfloat16, device=image.device) if want_txt_t else None
+            return img_r, txt_r, img_c, txt_c, self.prep_scalars(logit_scale, cap)
+        both = torch.empty((2, rows, d), dtype=torch.bfloat16, device=image.device)
+        img, txt = both[0], both[1]
         scal = self.empty((3,), torch.float32, image)
         a = PrepareArgs(_ptr(image), _ptr(text), _DTYPE_CODE[image.dtype], _ptr(logit_scale),
-                        float(cap) if cap is not None else -1.0, rows, d, ld_t, _ptr(img), _ptr(txt), _ptr(img_t),
-                        _ptr(txt_t), _ptr(scal))
+                        float(cap) if cap is not None else -1.0, rows, d, _ptr(img), _ptr(txt), _ptr(scal))
         with _DeviceGuard(image.device):
             self._check(self.lib.scl_prepare(C.byref(a), st), "scl_prepare")
-        self.launches += 3
-        return img, txt, img, txt, img_t, txt_t, scal
+        self.launches += 1
+        return img, txt, img, txt, scal
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
                     finalize_scalars, want_ranks=False, waits=None, positives=None):
@@ -384,7 +348,8 @@ class CudaOps:
         then issued once per phase (soft targets / image-rows pass / text-rows pass + reductions), each right after
         the wait for the one operand that phase reads.
         positives = (col, w, q) int32 / fp32 / fp32 [B_l, K+1] of the image rows (+ the same three of the text rows):
-        soft targets resolved on the data side; the builder phase is skipped."""
+        soft targets resolved on the data side (already passed through check_positives); the builder phase is
+        skipped."""
         st = self._stream(img_l)
         n, d = img_all.shape
         kp1 = k + 1
@@ -409,11 +374,11 @@ class CudaOps:
         stats_i, stats_t = small[:b_local], small[b_local:2 * b_local]
         sums6 = small[2 * b_local:2 * b_local + 2].reshape(-1)[:6]
         out4 = small[2 * b_local + 2]
-        ws_bytes = self.lib.scl_fwd_workspace_bytes(b_local, n, d, k, self.variant)
+        ws_bytes = self.lib.scl_fwd_workspace_bytes(b_local, n, d, k)
         if ws_bytes == 0:
             self._check(-2, "scl_fwd_workspace_bytes")
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        a = FwdArgs(_ptr(img_l), _ptr(txt_l), _ptr(img_all), _ptr(txt_all), b_local, n, d, rank, self.variant,
+        a = FwdArgs(_ptr(img_l), _ptr(txt_l), _ptr(img_all), _ptr(txt_all), b_local, n, d, rank,
                     _ptr(scalars), _ptr(ids[0]) if ids else None, _ptr(ids[1]) if ids else None,
                     _ptr(ids[2]) if ids else None, _ptr(ids[3]) if ids else None, k, float(alpha_scale), int(same),
                     float(c), float(w), int(finalize_scalars), _ptr(col_it), _ptr(w_it), _ptr(q_it), _ptr(col_ti),
@@ -433,19 +398,21 @@ class CudaOps:
                         wait()
                     if phase == 1 and positives is not None:
                         continue
+                    if phase == 1 and ids:  # the gathered id vectors exist only now (the wait de-interleaves them)
+                        a.img_ids_all, a.txt_ids_all = _ptr(ids[0]), _ptr(ids[1])
                     a.phases = phase
                     self._check(self.lib.scl_fwd_all(C.byref(a), st), "scl_fwd_all")
         built = 0 if positives is not None else (3 if k > 0 else 1) * (1 if same else 2)
-        self.launches += built + 5 + (1 if finalize_scalars else 0) + (2 if want_ranks else 0)
+        self.launches += built + 5 + (2 if want_ranks else 0)
         return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks
 
-    def backward_dir(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+    def backward_dir(self, x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                      b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local, split=False):
         """dX of the local rows for one direction: scl_bwd_dir (coefficients + fused tensor-core pass + sparse finish).
         With kernel timing on (bench.py roofline) the three launches are issued separately.
-        split: x_rows [m, 3 D], y_all [n, 3 D], y_all_t [2 D, ld] (fp32-accurate mode); the result is [m, D]."""
-        if self.kernel_events is not None or getattr(self, "cycle_buffers", None) is not None:
-            return self.bwd_rows(x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+        split: x_rows [m, 3 D], y_all [n, 3 D] (fp32-accurate mode); the result is [m, D]."""
+        if self.kernel_events is not None:
+            return self.bwd_rows(x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype,
                                  opp_q_local=opp_q_local, split=split)
         st = self._stream(x_rows)
@@ -453,21 +420,20 @@ class CudaOps:
         if split:
             d //= 3
         n = y_all.shape[0]
-        if y_all_t is None:  # mn_major: the library builds its second tensor map on y_all
-            y_all_t = y_all.new_empty((0, n))
-        ws_bytes = self.lib.scl_bwd_workspace_bytes(m, n, d, self.variant)
+        kp1 = pos_col.shape[1]
+        ws_bytes = self.lib.scl_bwd_workspace_bytes(m, n, d, kp1)
         if ws_bytes == 0:
             self._check(-2, "scl_bwd_workspace_bytes")
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x_rows.device)
         out = self.empty((m, d), out_dtype, x_rows)
-        a = BwdArgs(_ptr(x_rows), _ptr(y_all), _ptr(y_all_t) or _ptr(y_all), y_all_t.shape[1], m, n, d, rank, self.variant,
+        a = BwdArgs(_ptr(x_rows), _ptr(y_all), m, n, d, rank,
                     _ptr(row_stats), _ptr(col_stats), _ptr(pos_col), _ptr(pos_q), _ptr(opp_q_local),
-                    _ptr(opp_col_all), _ptr(opp_q_all), pos_col.shape[1], _ptr(gaps), _ptr(scalars), _ptr(grad_out),
+                    _ptr(opp_col_all), _ptr(opp_q_all), kp1, _ptr(gaps), _ptr(scalars), _ptr(grad_out),
                     float(c), float(w), float(mult), col_mode, _ptr(out), _DTYPE_CODE[out_dtype], _ptr(ws), ws_bytes,
                     int(split))
         with _DeviceGuard(x_rows.device):
             self._check(self.lib.scl_bwd_dir(C.byref(a), st), "scl_bwd_dir")
-        self.launches += 3 + (1 if col_mode != 0 else 0) + (1 if out_dtype != torch.float32 else 0)
+        self.launches += 3 + (3 if col_mode != 0 else 0)
         return out
 
     def exchange_records(self, parts, world, gather_fn):
@@ -494,7 +460,7 @@ class CudaOps:
         self.launches += 2
         return outs
 
-    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+    def bwd_rows(self, x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None,
                  split=False):
         """dX for the local rows: coefficients + fused tensor-core pass + sparse finish."""
@@ -503,32 +469,30 @@ class CudaOps:
         if split:
             d //= 3
         n = y_all.shape[0]
-        if y_all_t is None:  # mn_major
-            y_all_t = y_all.new_empty((0, n))
+        kp1 = pos_col.shape[1]
         plan = self.bwd_plan(m, n, d, split)
         row_coef = self.empty((plan.m_pad, 4), torch.float32, x_rows)
         col_coef = self.empty((plan.n_pad, 4), torch.float32, x_rows)
         partial = self.empty((plan.chunks, plan.m_pad, d), torch.float32, x_rows)
-        dx32 = self.empty((m, d), torch.float32, x_rows)
-        out = dx32 if out_dtype == torch.float32 else self.empty((m, d), out_dtype, x_rows)
+        out = self.empty((m, d), out_dtype, x_rows)
+        fin_bytes = self.lib.scl_bwd_finish_workspace_bytes(n, b_local, kp1) if col_mode != 0 else 0
+        fin_ws = self.empty((fin_bytes,), torch.uint8, x_rows) if fin_bytes else None
         if opp_q_local is None:  # single rank: the gathered opposite list IS the local one
             opp_q_local = opp_q_all[rank * b_local:(rank + 1) * b_local]
         with _DeviceGuard(x_rows.device):
             self._check(self.lib.scl_bwd_coeffs(_ptr(row_stats), m, _ptr(col_stats), n, C.byref(plan), b_local, rank,
                                                 _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c), float(w),
                                                 float(mult), col_mode, _ptr(pos_q), _ptr(opp_q_local),
-                                                pos_col.shape[1], _ptr(row_coef), _ptr(col_coef), st),
+                                                kp1, _ptr(row_coef), _ptr(col_coef), st),
                         "scl_bwd_coeffs")
             self._check(self._timed("bwd_rows", x_rows.device, lambda: self.lib.scl_bwd_rows(
-                _ptr(x_rows), m, _ptr(y_all), _ptr(y_all_t) or _ptr(y_all), y_all_t.shape[1], n, d, rank * b_local,
-                _ptr(scalars),
-                C.byref(plan),
-                _ptr(row_coef), _ptr(col_coef), _ptr(partial), _ptr(self._cycles("bwd", plan, x_rows)), st)),
+                _ptr(x_rows), m, _ptr(y_all), n, d, rank * b_local, _ptr(scalars), C.byref(plan),
+                _ptr(row_coef), _ptr(col_coef), _ptr(partial), st)),
                 "scl_bwd_rows")
             self._check(self.lib.scl_bwd_finish(_ptr(partial), C.byref(plan), m, d, _ptr(y_all), _ptr(pos_col),
-                                                _ptr(pos_q), pos_col.shape[1], _ptr(opp_col_all), _ptr(opp_q_all), n,
+                                                _ptr(pos_q), kp1, _ptr(opp_col_all), _ptr(opp_q_all), n,
                                                 b_local, rank, _ptr(gaps), _ptr(scalars), _ptr(grad_out), float(c),
-                                                float(w), float(mult), col_mode, _ptr(dx32), _ptr(out),
+                                                float(w), float(mult), col_mode, _ptr(fin_ws), fin_bytes, _ptr(out),
                                                 _DTYPE_CODE[out_dtype], st), "scl_bwd_finish")
-        self.launches += 3 + (1 if col_mode != 0 else 0) + (1 if out_dtype != torch.float32 else 0)
+        self.launches += 3 + (3 if col_mode != 0 else 0)
         return out

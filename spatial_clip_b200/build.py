@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libscl_b200.so"
-SOURCES = ["scl_api.cu", "scl_fwd.cu", "scl_bwd.cu", "scl_fwd2.cu", "scl_bwd2.cu", "scl_aux.cu", "scl_split.cu", "scl_rank.cu"]
+SOURCES = ["scl_api.cu", "scl_fwd2.cu", "scl_bwd2.cu", "scl_aux.cu", "scl_split.cu", "scl_rank.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

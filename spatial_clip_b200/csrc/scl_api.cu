@@ -4,7 +4,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
-#include <cstdlib>
 
 #include "../../include/scl_b200.h"
 #include "scl_kernels.h"
@@ -59,37 +58,16 @@ int num_sms_or_default() {
   return sms;
 }
 
-constexpr int kDefaultVariant = 1;
-int resolve_variant(int variant) {
-  if (variant == 0 || variant == 1) return variant;
-  const char* e = std::getenv("SCL_VARIANT");
-  if (e != nullptr && (e[0] == '0' || e[0] == '1') && e[1] == 0) return e[0] - '0';
-  return kDefaultVariant;
-}
-
-// Output width D: D % 64 == 0 up to 512; 768 and 1024-class widths (D % 256 == 0 up to 1024) run on the CTA-pair
-// kernels only (two D slices in the backward).
-bool experimental_shapes() {
-  // widths whose slice layout (e.g. a 64-column accumulator group) has not been run on a B200 yet
-  static const bool on = [] {
-    const char* e = std::getenv("SCL_EXPERIMENTAL_SHAPES");
-    return e != nullptr && e[0] == '1' && e[1] == 0;
-  }();
-  return on;
-}
-bool shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
-  if (m_rows < 1 || n_cols < 1 || d < 64) return false;
-  if (d <= 512) return d % 64 == 0;
-  if (variant != 1) return false;
-  if (d <= 1024 && d % 256 == 0) return true;
-  // 640 / 1152 / 1280 / 1536 (other open_clip widths): same kernels, more D slices
-  return experimental_shapes() && d <= 1536 && d % 64 == 0 && scl::bwd_pair_d_slices(d) > 0;
+// Output width D of the backward: D % 64 == 0 up to 512 (one pass), or up to 1536 with an equal cut into slices of at
+// most 512 columns (640, 768, 1024, 1152, 1280, 1536: one pass per slice).
+bool shape_ok(int m_rows, int n_cols, int d) {
+  if (m_rows < 1 || n_cols < 1 || d < 64 || d % 64 != 0) return false;
+  return d <= 512 || (d <= 1536 && scl::bwd_pair_d_slices(d) > 0);
 }
 // Contraction length of the forward pass: as above, plus the K-concatenated operands of the fp32-accurate mode
-// (3 D, so up to 3072) -- beyond 512 the CTA-pair kernel streams X with Y and any multiple of 64 works.
-bool fwd_shape_ok(int m_rows, int n_cols, int d, int variant = 1) {
-  if (m_rows < 1 || n_cols < 1 || d < 64 || d % 64 != 0) return false;
-  return d <= 512 || (variant == 1 && d <= 3072);
+// (3 D, so up to 4608) -- beyond 512 the kernel streams X with Y and any multiple of 64 works.
+bool fwd_shape_ok(int m_rows, int n_cols, int d) {
+  return m_rows >= 1 && n_cols >= 1 && d >= 64 && d % 64 == 0 && d <= 4608;
 }
 
 }  // namespace
@@ -103,8 +81,8 @@ const char* scl_error_string(int code) {
     case SCL_OK: return "ok";
     case SCL_ERR_INVALID_ARG: return "invalid argument (null / misaligned pointer or bad size)";
     case SCL_ERR_UNSUPPORTED_SHAPE:
-      return "unsupported shape (need rows >= 1 and D % 64 == 0 up to 512, or D % 256 == 0 up to 1024 on the CTA-pair "
-             "kernels; the fp32-accurate mode needs the CTA-pair kernels)";
+      return "unsupported shape (need rows >= 1 and D % 64 == 0 up to 512, or up to 1536 with an equal cut into slices "
+             "of at most 512 columns, each a multiple of 64)";
     case SCL_ERR_NO_DRIVER_ENTRY: return "cuTensorMapEncodeTiled not available from the CUDA driver";
     case SCL_ERR_TENSOR_MAP: return "cuTensorMapEncodeTiled rejected the tensor map";
     case SCL_ERR_NOT_SM100: return "device is not compute capability 10.x (kernels are sm_100a only)";
@@ -126,63 +104,39 @@ int scl_check_device(int* num_sms) {
   return major == 10 ? SCL_OK : SCL_ERR_NOT_SM100;
 }
 
-int scl_fwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
+int scl_fwd_plan(int m_rows, int n_cols, int d, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
   if (!fwd_shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   int tpc = 0;
-  plan->variant = resolve_variant(variant);
   plan->split = 0;
-  if (!fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
-  if (plan->variant == 1) {
-    plan->chunks = scl::fwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
-    plan->m_pad = (m_rows + 255) / 256 * 256;
-  } else {
-    plan->chunks = scl::fwd_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
-    plan->m_pad = (m_rows + 127) / 128 * 128;
-  }
+  plan->chunks = scl::fwd_pair_pick_chunks(m_rows, n_cols, num_sms_or_default(), &tpc);
+  plan->m_pad = (m_rows + 255) / 256 * 256;
   plan->tiles_per_chunk = tpc;
-  plan->n_slots = (plan->variant == 1 ? 4 : 2) * plan->chunks;
+  plan->n_slots = 4 * plan->chunks;
   plan->n_pad = (n_cols + 255) / 256 * 256;
   plan->d_split = 1;
   return SCL_OK;
 }
 
-int scl_bwd_plan(int m_rows, int n_cols, int d, int variant, scl_plan* plan) {
-  return scl_bwd_plan_ex(m_rows, n_cols, d, variant, 0, plan);
-}
-
-int scl_bwd_plan_ex(int m_rows, int n_cols, int d, int variant, int split, scl_plan* plan) {
+int scl_bwd_plan(int m_rows, int n_cols, int d, int split, scl_plan* plan) {
   if (plan == nullptr) return SCL_ERR_INVALID_ARG;
   if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
-  int tpc = 0, nds = 0, dn = 0;
-  plan->variant = resolve_variant(variant);
+  int tpc = 0;
   plan->split = split ? 1 : 0;
-  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
-  if (plan->split && plan->variant != 1) return SCL_ERR_UNSUPPORTED_SHAPE;
   plan->m_pad = (m_rows + 127) / 128 * 128;
   plan->n_slots = 0;
-  if (plan->variant == 1) {
-    plan->chunks = scl::bwd_pair_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
-    plan->n_pad = (n_cols + 255) / 256 * 256;
-    plan->d_split = scl::bwd_pair_d_slices(d);
-  } else {
-    scl::bwd_pick_split(d, &nds, &dn);
-    if (dn % 32 != 0) return SCL_ERR_UNSUPPORTED_SHAPE;
-    plan->chunks = scl::bwd_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
-    plan->n_pad = (n_cols + 127) / 128 * 128;
-    plan->d_split = nds;
-  }
+  plan->chunks = scl::bwd_pair_pick_chunks(m_rows, n_cols, d, num_sms_or_default(), &tpc);
+  plan->n_pad = (n_cols + 255) / 256 * 256;
+  plan->d_split = scl::bwd_pair_d_slices(d);
   plan->tiles_per_chunk = tpc;
   return SCL_OK;
 }
 
-int scl_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t, int normalize,
-                  void* stream) {
-  if (x == nullptr || (y == nullptr && y_t == nullptr) || rows < 0 || d <= 0 || d % 64 != 0 || src_dtype < 0 ||
-      src_dtype > 2 || (y_t != nullptr && ld_t < rows) || (reinterpret_cast<uintptr_t>(x) & 15) != 0 ||
-      (reinterpret_cast<uintptr_t>(y) & 7) != 0 || (reinterpret_cast<uintptr_t>(y_t) & 15) != 0)
+int scl_cast_bf16(const void* x, int src_dtype, void* y, int rows, int d, int normalize, void* stream) {
+  if (x == nullptr || y == nullptr || rows < 0 || d <= 0 || d % 64 != 0 || src_dtype < 0 || src_dtype > 2 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0)
     return SCL_ERR_INVALID_ARG;
-  return cuda_rc(scl::launch_cast_bf16(x, src_dtype, y, y_t, rows, d, ld_t, normalize, static_cast<cudaStream_t>(stream)));
+  return cuda_rc(scl::launch_cast_bf16(x, src_dtype, y, rows, d, normalize, static_cast<cudaStream_t>(stream)));
 }
 
 int scl_prep_scalars(const float* logit_scale, float cap, float* scalars3, void* stream) {
@@ -206,24 +160,19 @@ int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr
 }
 
 int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
-                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, long long* dbg_cycles,
-                     void* stream) {
+                     const scl_plan* plan, void* partial, float* dbg_z, int dbg_ld, void* stream) {
   if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr)
     return SCL_ERR_INVALID_ARG;
-  if (!fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!fwd_shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_rows, tm_cols;
   int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
   if (rc != SCL_OK) return rc;
-  rc = make_map(&tm_cols, y_cols, d, n_cols, d, plan->variant == 1 ? 128 : 256);
+  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
   if (rc != SCL_OK) return rc;
-  if (plan->variant == 1)
-    return cuda_rc(scl::launch_fwd_rowstats_pair(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks,
-                                                 plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
-                                                 static_cast<float4*>(partial), dbg_z, dbg_ld, dbg_cycles,
-                                                 static_cast<cudaStream_t>(stream)));
-  return cuda_rc(scl::launch_fwd_rowstats(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks, plan->tiles_per_chunk,
-                                          plan->m_pad, scalars3 + 1, static_cast<float4*>(partial), dbg_z, dbg_ld,
-                                          static_cast<cudaStream_t>(stream)));
+  return cuda_rc(scl::launch_fwd_rowstats_pair(tm_rows, tm_cols, m_rows, n_cols, d, plan->chunks,
+                                               plan->tiles_per_chunk, plan->m_pad, scalars3 + 1,
+                                               static_cast<float4*>(partial), dbg_z, dbg_ld,
+                                               static_cast<cudaStream_t>(stream)));
 }
 
 int scl_fwd_rowstats_ranks(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
@@ -232,7 +181,7 @@ int scl_fwd_rowstats_ranks(const void* x_rows, int m_rows, const void* y_cols, i
   if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || partial == nullptr ||
       diag_z == nullptr || rank_partial == nullptr || ranks == nullptr || first_col < 0 || first_col + m_rows > n_cols)
     return SCL_ERR_INVALID_ARG;
-  if (plan->variant != 1 || !fwd_shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  if (!fwd_shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = cuda_rc(scl::launch_retrieval_diag(x_rows, m_rows, y_cols, d, first_col, diag_z, st));
   if (rc != SCL_OK) return rc;
@@ -260,12 +209,21 @@ int scl_row_finalize(const void* partial, const scl_plan* plan, int m_rows, int 
                                           static_cast<cudaStream_t>(stream)));
 }
 
+int scl_check_positives(const int32_t* col_in, const float* q_in, int b_local, int k_plus_1, int n_global, int rank,
+                        int32_t* col_out, float* q_out, int* flag, void* stream) {
+  if (col_in == nullptr || q_in == nullptr || col_out == nullptr || q_out == nullptr || flag == nullptr ||
+      b_local < 1 || k_plus_1 < 1 || n_global < b_local || rank < 0)
+    return SCL_ERR_INVALID_ARG;
+  return cuda_rc(scl::launch_check_positives(col_in, q_in, b_local, k_plus_1, n_global, rank, col_out, q_out, flag,
+                                             static_cast<cudaStream_t>(stream)));
+}
+
 int scl_reduce_rows(const void* stats_img, const void* stats_txt, int m_rows, const float* scalars3, float* sums6,
                     void* stream) {
   if (stats_img == nullptr || stats_txt == nullptr || scalars3 == nullptr || sums6 == nullptr || m_rows < 1)
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_reduce_rows(static_cast<const float4*>(stats_img), static_cast<const float4*>(stats_txt),
-                                         m_rows, scalars3, sums6, static_cast<cudaStream_t>(stream)));
+                                         m_rows, scalars3, sums6, 0.f, 0.f, nullptr, static_cast<cudaStream_t>(stream)));
 }
 
 int scl_loss_scalars(const float* sums6, const float* scalars3, float c, float w, float* out4, void* stream) {
@@ -288,61 +246,47 @@ int scl_bwd_coeffs(const void* row_stats, int m_rows, const void* col_stats, int
                                         static_cast<cudaStream_t>(stream)));
 }
 
-int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, const void* y_cols_t, int ld_t, int n_cols,
-                 int d, int diag_col0, const float* scalars3, const scl_plan* plan, const void* row_coef,
-                 const void* col_coef, float* dx_partial, long long* dbg_cycles, void* stream) {
-  if (x_rows == nullptr || y_cols == nullptr || y_cols_t == nullptr || scalars3 == nullptr || plan == nullptr ||
-      row_coef == nullptr || col_coef == nullptr || dx_partial == nullptr || ld_t < n_cols)
+int scl_bwd_rows(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, int diag_col0,
+                 const float* scalars3, const scl_plan* plan, const void* row_coef, const void* col_coef,
+                 float* dx_partial, void* stream) {
+  if (x_rows == nullptr || y_cols == nullptr || scalars3 == nullptr || plan == nullptr || row_coef == nullptr ||
+      col_coef == nullptr || dx_partial == nullptr)
     return SCL_ERR_INVALID_ARG;
-  if (!shape_ok(m_rows, n_cols, d, plan->variant)) return SCL_ERR_UNSUPPORTED_SHAPE;
-  int nds = 0, dn = 0;
-  scl::bwd_pick_split(d, &nds, &dn);
-  CUtensorMap tm_rows, tm_cols, tm_cols_t;
-  if (plan->variant == 1) {
-    // fp32-accurate mode: x_rows / y_cols are the K-concatenated operands [., 3 d], y_cols_t the stacked [2 d, ld_t]
-    const int kd = plan->split ? 3 * d : d;
-    int rc = make_map(&tm_rows, x_rows, kd, m_rows, kd, 64);
-    if (rc != SCL_OK) return rc;
-    rc = make_map(&tm_cols, y_cols, kd, n_cols, kd, 128);
-    if (rc != SCL_OK) return rc;
-    if (!plan->split && scl::bwd_pair_mn_major())  // SCL_BWD_MN=1: the gradient GEMM reads Y itself (y_cols_t unused)
-      rc = make_map(&tm_cols_t, y_cols, d, n_cols, d, 64);
-    else
-      rc = make_map(&tm_cols_t, y_cols_t, n_cols, plan->split ? 2 * d : d, ld_t, 128);
-    if (rc != SCL_OK) return rc;
-    return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
-                                             plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
-                                             static_cast<const float4*>(row_coef),
-                                             static_cast<const float4*>(col_coef), dx_partial, dbg_cycles,
-                                             plan->split, static_cast<cudaStream_t>(stream)));
-  }
-  if (plan->split) return SCL_ERR_UNSUPPORTED_SHAPE;
-  int rc = make_map(&tm_rows, x_rows, d, m_rows, d, 128);
+  if (!shape_ok(m_rows, n_cols, d)) return SCL_ERR_UNSUPPORTED_SHAPE;
+  // fp32-accurate mode: x_rows / y_cols are the K-concatenated operands [., 3 d]
+  const int kd = plan->split ? 3 * d : d;
+  CUtensorMap tm_rows, tm_cols, tm_cols_mn;
+  int rc = make_map(&tm_rows, x_rows, kd, m_rows, kd, 64);
   if (rc != SCL_OK) return rc;
-  rc = make_map(&tm_cols, y_cols, d, n_cols, d, 128);
+  rc = make_map(&tm_cols, y_cols, kd, n_cols, kd, 128);
   if (rc != SCL_OK) return rc;
-  rc = make_map(&tm_cols_t, y_cols_t, n_cols, d, ld_t, static_cast<uint32_t>(dn));
+  rc = make_map(&tm_cols_mn, y_cols, kd, n_cols, kd, 64);  // the same matrix in {64 d, 64 j} boxes (MN-major operand)
   if (rc != SCL_OK) return rc;
-  return cuda_rc(scl::launch_bwd_rows(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, plan->chunks,
-                                      plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
-                                      static_cast<const float4*>(row_coef), static_cast<const float4*>(col_coef),
-                                      dx_partial, static_cast<cudaStream_t>(stream)));
+  return cuda_rc(scl::launch_bwd_rows_pair(tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d, plan->chunks,
+                                           plan->tiles_per_chunk, plan->m_pad, diag_col0, scalars3 + 1,
+                                           static_cast<const float4*>(row_coef), static_cast<const float4*>(col_coef),
+                                           dx_partial, plan->split, static_cast<cudaStream_t>(stream)));
+}
+
+size_t scl_bwd_finish_workspace_bytes(int n_global, int b_local, int k_plus_1) {
+  return scl::bwd_finish_workspace_bytes(n_global, b_local, k_plus_1);
 }
 
 int scl_bwd_finish(const float* dx_partial, const scl_plan* plan, int m_rows, int d, const void* y_all,
                    const int32_t* pos_col, const float* pos_q, int k_plus_1, const int32_t* opp_col_all,
                    const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                    const float* scalars3, const float* grad_out, float c, float w, float mult, int col_mode,
-                   float* dx32, void* dx_out, int out_dtype, void* stream) {
+                   void* workspace, size_t workspace_bytes, void* dx_out, int out_dtype, void* stream) {
   if (dx_partial == nullptr || plan == nullptr || y_all == nullptr || pos_col == nullptr || pos_q == nullptr ||
-      gaps == nullptr || scalars3 == nullptr || grad_out == nullptr || dx32 == nullptr || k_plus_1 < 1 ||
-      out_dtype < 0 || out_dtype > 2 || (out_dtype != 0 && dx_out == nullptr) ||
-      (col_mode != 0 && (opp_col_all == nullptr || opp_q_all == nullptr)))
+      gaps == nullptr || scalars3 == nullptr || grad_out == nullptr || dx_out == nullptr || k_plus_1 < 1 ||
+      k_plus_1 > 32 || out_dtype < 0 || out_dtype > 2 ||
+      (col_mode != 0 && (opp_col_all == nullptr || opp_q_all == nullptr || workspace == nullptr ||
+                         workspace_bytes < scl::bwd_finish_workspace_bytes(n_global, b_local, k_plus_1))))
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_bwd_finish(dx_partial, plan->chunks, plan->m_pad, m_rows, d, y_all, pos_col, pos_q,
                                         k_plus_1, opp_col_all, opp_q_all, n_global, b_local, rank, gaps, scalars3,
-                                        grad_out, c, w, mult, col_mode, plan->split, dx32, dx_out, out_dtype,
-                                        static_cast<cudaStream_t>(stream)));
+                                        grad_out, c, w, mult, col_mode, plan->split, workspace, workspace_bytes, dx_out,
+                                        out_dtype, static_cast<cudaStream_t>(stream)));
 }
 
 namespace {
@@ -351,18 +295,18 @@ inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 
 int scl_prepare(const scl_prepare_args* a, void* stream) {
   if (a == nullptr || a->image == nullptr || a->text == nullptr || a->image_bf16 == nullptr ||
-      a->text_bf16 == nullptr || a->scalars3 == nullptr || a->logit_scale == nullptr)
+      a->text_bf16 == nullptr || a->scalars3 == nullptr || a->logit_scale == nullptr || a->rows < 1 || a->d < 64 ||
+      a->d % 64 != 0 || a->src_dtype < 0 || a->src_dtype > 2 ||
+      ((reinterpret_cast<uintptr_t>(a->image) | reinterpret_cast<uintptr_t>(a->text) |
+        reinterpret_cast<uintptr_t>(a->image_bf16) | reinterpret_cast<uintptr_t>(a->text_bf16)) & 15) != 0)
     return SCL_ERR_INVALID_ARG;
-  int rc = scl_prep_scalars(a->logit_scale, a->cap, a->scalars3, stream);
-  if (rc != SCL_OK) return rc;
-  rc = scl_cast_bf16(a->image, a->src_dtype, a->image_bf16, a->image_bf16_t, a->rows, a->d, a->ld_t, 0, stream);
-  if (rc != SCL_OK) return rc;
-  return scl_cast_bf16(a->text, a->src_dtype, a->text_bf16, a->text_bf16_t, a->rows, a->d, a->ld_t, 0, stream);
+  return cuda_rc(scl::launch_prepare(a->image, a->text, a->src_dtype, a->rows, a->d, a->image_bf16, a->text_bf16,
+                                     a->logit_scale, a->cap, a->scalars3, static_cast<cudaStream_t>(stream)));
 }
 
-size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int variant) {
+size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k) {
   scl_plan p;
-  if (scl_fwd_plan(b_local, n_global, d, variant, &p) != SCL_OK) return 0;
+  if (scl_fwd_plan(b_local, n_global, d, &p) != SCL_OK) return 0;
   const size_t partial = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
   const size_t hash = k > 0 ? align256(scl::positives_hash_bytes(n_global)) : 0;
   // + the retrieval-rank work areas (rank partials, own-pair similarities); small, so always included
@@ -373,9 +317,9 @@ size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k, int vari
 int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   if (a == nullptr || a->workspace == nullptr) return SCL_ERR_INVALID_ARG;
   scl_plan p;
-  int rc = scl_fwd_plan(a->b_local, a->n_global, a->d, a->variant, &p);
+  int rc = scl_fwd_plan(a->b_local, a->n_global, a->d, &p);
   if (rc != SCL_OK) return rc;
-  if (a->workspace_bytes < scl_fwd_workspace_bytes(a->b_local, a->n_global, a->d, a->k, a->variant))
+  if (a->workspace_bytes < scl_fwd_workspace_bytes(a->b_local, a->n_global, a->d, a->k))
     return SCL_ERR_INVALID_ARG;
   const size_t partial_bytes = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
   char* ws = static_cast<char*>(a->workspace);
@@ -406,7 +350,7 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
                                   a->rank * a->b_local, diag_z, rank_partial, a->ranks_out, stream);
     else
       rc = scl_fwd_rowstats(a->img_l, a->b_local, a->txt_all, a->n_global, a->d, a->scalars3, &p, part_i, nullptr, 0,
-                            nullptr, stream);
+                            stream);
     if (rc != SCL_OK) return rc;
     rc = scl_row_finalize(part_i, &p, a->b_local, a->d, a->img_l, a->txt_all, a->col_it, a->q_it, a->k + 1,
                           a->stats_i, stream);
@@ -414,30 +358,33 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   }
   if (!(phases & 4)) return SCL_OK;
   rc = scl_fwd_rowstats(a->txt_l, a->b_local, a->img_all, a->n_global, a->d, a->scalars3, &p, part_t, nullptr, 0,
-                        nullptr, stream);
+                        stream);
   if (rc != SCL_OK) return rc;
   rc = scl_row_finalize(part_t, &p, a->b_local, a->d, a->txt_l, a->img_all, a->col_ti, a->q_ti, a->k + 1, a->stats_t,
                         stream);
   if (rc != SCL_OK) return rc;
-  rc = scl_reduce_rows(a->stats_i, a->stats_t, a->b_local, a->scalars3, a->sums6, stream);
-  if (rc != SCL_OK) return rc;
-  if (a->finalize_scalars) rc = scl_loss_scalars(a->sums6, a->scalars3, a->c, a->w, a->out4, stream);
-  return rc;
+  if (a->stats_i == nullptr || a->stats_t == nullptr || a->sums6 == nullptr || (a->finalize_scalars && a->out4 == nullptr))
+    return SCL_ERR_INVALID_ARG;
+  // row reductions (+ the loss scalars in the same launch)
+  return cuda_rc(scl::launch_reduce_rows(static_cast<const float4*>(a->stats_i), static_cast<const float4*>(a->stats_t),
+                                         a->b_local, a->scalars3, a->sums6, a->c, a->w,
+                                         a->finalize_scalars ? a->out4 : nullptr, static_cast<cudaStream_t>(stream)));
 }
 
-size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int variant) {
+size_t scl_bwd_workspace_bytes(int b_local, int n_global, int d, int k_plus_1) {
   scl_plan p;
-  if (scl_bwd_plan(b_local, n_global, d, variant, &p) != SCL_OK) return 0;
+  if (scl_bwd_plan(b_local, n_global, d, 0, &p) != SCL_OK) return 0;
   return align256(static_cast<size_t>(p.m_pad) * 16) + align256(static_cast<size_t>(p.n_pad) * 16) +
-         align256(static_cast<size_t>(p.chunks) * p.m_pad * d * 4) + align256(static_cast<size_t>(b_local) * d * 4);
+         align256(static_cast<size_t>(p.chunks) * p.m_pad * d * 4) +
+         align256(scl::bwd_finish_workspace_bytes(n_global, b_local, k_plus_1));
 }
 
 int scl_bwd_dir(const scl_bwd_args* a, void* stream) {
   if (a == nullptr || a->workspace == nullptr || a->dx_out == nullptr) return SCL_ERR_INVALID_ARG;
   scl_plan p;
-  int rc = scl_bwd_plan_ex(a->b_local, a->n_global, a->d, a->variant, a->split, &p);
+  int rc = scl_bwd_plan(a->b_local, a->n_global, a->d, a->split, &p);
   if (rc != SCL_OK) return rc;
-  if (a->workspace_bytes < scl_bwd_workspace_bytes(a->b_local, a->n_global, a->d, a->variant))
+  if (a->workspace_bytes < scl_bwd_workspace_bytes(a->b_local, a->n_global, a->d, a->k_plus_1))
     return SCL_ERR_INVALID_ARG;
   char* ws = static_cast<char*>(a->workspace);
   void* row_coef = ws;
@@ -446,17 +393,17 @@ int scl_bwd_dir(const scl_bwd_args* a, void* stream) {
   ws += align256(static_cast<size_t>(p.n_pad) * 16);
   float* partial = reinterpret_cast<float*>(ws);
   ws += align256(static_cast<size_t>(p.chunks) * p.m_pad * a->d * 4);
-  float* dx32 = a->out_dtype == 0 ? static_cast<float*>(a->dx_out) : reinterpret_cast<float*>(ws);
+  const size_t fin_bytes = scl::bwd_finish_workspace_bytes(a->n_global, a->b_local, a->k_plus_1);
   rc = scl_bwd_coeffs(a->row_stats, a->b_local, a->col_stats_all, a->n_global, &p, a->b_local, a->rank, a->gaps,
                       a->scalars3, a->grad_out, a->c, a->w, a->mult, a->col_mode, a->pos_q, a->opp_q_local,
                       a->k_plus_1, row_coef, col_coef, stream);
   if (rc != SCL_OK) return rc;
-  rc = scl_bwd_rows(a->x_rows, a->b_local, a->y_all, a->y_all_t, a->ld_t, a->n_global, a->d, a->rank * a->b_local,
-                    a->scalars3, &p, row_coef, col_coef, partial, nullptr, stream);
+  rc = scl_bwd_rows(a->x_rows, a->b_local, a->y_all, a->n_global, a->d, a->rank * a->b_local, a->scalars3, &p,
+                    row_coef, col_coef, partial, stream);
   if (rc != SCL_OK) return rc;
   return scl_bwd_finish(partial, &p, a->b_local, a->d, a->y_all, a->pos_col, a->pos_q, a->k_plus_1, a->opp_col_all,
                         a->opp_q_all, a->n_global, a->b_local, a->rank, a->gaps, a->scalars3, a->grad_out, a->c, a->w,
-                        a->mult, a->col_mode, dx32, a->dx_out, a->out_dtype, stream);
+                        a->mult, a->col_mode, ws, fin_bytes, a->dx_out, a->out_dtype, stream);
 }
 
 int scl_split_bf16(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d, void* stream) {
@@ -465,13 +412,6 @@ int scl_split_bf16(const void* x, int src_dtype, void* rows_out, void* cols_out,
       (reinterpret_cast<uintptr_t>(rows_out) & 15) != 0 || (reinterpret_cast<uintptr_t>(cols_out) & 15) != 0)
     return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_split_cast(x, src_dtype, rows_out, cols_out, rows, d, static_cast<cudaStream_t>(stream)));
-}
-
-int scl_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, void* stream) {
-  if (cols_all == nullptr || out_t == nullptr || n_rows < 0 || d <= 0 || d % 64 != 0 || ld_t < n_rows ||
-      (reinterpret_cast<uintptr_t>(cols_all) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_t) & 15) != 0)
-    return SCL_ERR_INVALID_ARG;
-  return cuda_rc(scl::launch_transpose_split(cols_all, n_rows, d, ld_t, out_t, static_cast<cudaStream_t>(stream)));
 }
 
 int scl_unpack_records(const float* gathered, int world, int rec_floats, int n_comp, float* const* outs,

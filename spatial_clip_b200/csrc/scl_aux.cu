@@ -18,20 +18,6 @@ namespace scl {
 // cast / normalise / transpose
 // =====================================================================================
 template <typename T>
-__device__ __forceinline__ float load_as_float(const T* p, size_t i);
-template <>
-__device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) { return p[i]; }
-template <>
-__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
-  return __bfloat162float(p[i]);
-}
-template <>
-__device__ __forceinline__ float load_as_float<__half>(const __half* p, size_t i) { return __half2float(p[i]); }
-
-// One CTA handles a [64 rows x d] slab in [64 x 64] tiles: 16-byte global loads (4 fp32 / 8 bf16 per thread),
-// optional per-row 1/||x||, 8-byte row-major bf16 stores, and the transposed copy y_t[d][ld_t] written as
-// 16-byte vectors of 8 consecutive rows assembled from a padded smem tile.
-template <typename T>
 __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
 template <>
 __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
@@ -52,95 +38,103 @@ __device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+__device__ __forceinline__ uint2 pack4_bf16(const float (&v)[4], float s) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0] * s, v[1] * s);
+  const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2] * s, v[3] * s);
+  uint2 p;
+  p.x = *reinterpret_cast<const uint32_t*>(&lo);
+  p.y = *reinterpret_cast<const uint32_t*>(&hi);
+  return p;
+}
 
+// Streaming cast of up to two [rows, d] matrices (blockIdx.y selects the matrix) to bf16: one thread = 8 consecutive
+// elements (two 16-byte loads for fp32, one 16-byte store), grid-stride.  Block (0, 0) also writes the scalars when
+// logit_scale != nullptr (scl_prepare: cap + both casts in one launch).
 template <typename T>
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                        __nv_bfloat16* __restrict__ y_t, int rows, int d, int ld_t,
-                                                        int normalize) {
-  __shared__ float inv_norm[64];
-  // [row][col + 8 * (row / 8)]: 240-byte pitch plus a per-8-row-group skew makes the 8-row column gathers of the
-  // transposed store hit 8 different banks
-  __shared__ __nv_bfloat16 tile[64][120];
-  const int r0 = blockIdx.x * 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (normalize) {
-    for (int rr = warp; rr < 64; rr += 8) {
-      const int r = r0 + rr;
-      float ss = 0.f;
-      if (r < rows) {
-        for (int c = lane * 4; c < d; c += 128) {
-          float v[4];
-          load4(x + static_cast<size_t>(r) * d + c, v);
-          ss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], ss))));
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) inv_norm[rr] = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (open_clip model.py:328,345)
-    }
-  } else if (threadIdx.x < 64) {
-    inv_norm[threadIdx.x] = 1.f;
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const T* __restrict__ x0, __nv_bfloat16* __restrict__ y0,
+                                                        const T* __restrict__ x1, __nv_bfloat16* __restrict__ y1,
+                                                        size_t n_oct, const float* __restrict__ logit_scale, float cap,
+                                                        float* __restrict__ scalars) {
+  if (logit_scale != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const float s = logit_scale[0];
+    const float s_eff = cap > 0.f ? fminf(s, cap) : s;
+    scalars[0] = s_eff;
+    scalars[1] = s_eff * kLog2e;
+    scalars[2] = s;
   }
-  __syncthreads();
-  // thread -> (row rr = tid / 16 + 16 * pass, 4 columns at 4 * (tid % 16))
-  const int tc = (threadIdx.x & 15) * 4;
-  const int tr = threadIdx.x >> 4;
-  // transposed stores: thread -> (column cc = tid / 8 + 32 * pass, 8 rows at 8 * (tid % 8))
-  const int sr = (threadIdx.x & 7) * 8;
-  const int sc = threadIdx.x >> 3;
-  const bool full_rows = r0 + 64 <= rows && (ld_t % 8) == 0;
-  for (int c0 = 0; c0 < d; c0 += 64) {
+  const T* x = blockIdx.y == 0 ? x0 : x1;
+  __nv_bfloat16* y = blockIdx.y == 0 ? y0 : y1;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_oct;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a[4], b[4];
+    load4(x + i * 8, a);
+    load4(x + i * 8 + 4, b);
+    const uint2 pa = pack4_bf16(a, 1.f), pb = pack4_bf16(b, 1.f);
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(pa.x, pa.y, pb.x, pb.y);
+  }
+}
+// F.normalize(x, dim=-1) + cast (producer contract, open_clip model.py:326-345): one warp per row, the row is read
+// twice (the second read hits L1/L2)
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                                  int rows, int d) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + static_cast<size_t>(row) * d;
+  float ss = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4];
+    load4(xr + c, v);
+    ss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], ss))));
+  }
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int rr = tr + 16 * pass;
-      const int r = r0 + rr;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (r < rows) load4(x + static_cast<size_t>(r) * d + c0 + tc, v);
-      const float s = inv_norm[rr];
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0] * s, v[1] * s);
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2] * s, v[3] * s);
-      uint2 packed;
-      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
-      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(&tile[rr][tc + 8 * (rr >> 3)]) = packed;
-      if (y != nullptr && r < rows) *reinterpret_cast<uint2*>(y + static_cast<size_t>(r) * d + c0 + tc) = packed;
-    }
-    if (y_t != nullptr) {
-      __syncthreads();
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int cc = sc + 32 * pass;
-        __nv_bfloat16 col[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) col[k] = tile[sr + k][cc + sr];
-        __nv_bfloat16* dst = y_t + static_cast<size_t>(c0 + cc) * ld_t + r0 + sr;
-        if (full_rows) {
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(col);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (r0 + sr + k < rows) dst[k] = col[k];
-        }
-      }
-      __syncthreads();
-    }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4];
+    load4(xr + c, v);
+    *reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * d + c) = pack4_bf16(v, inv);
   }
 }
 
-cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t,
-                             int normalize, cudaStream_t stream) {
-  if (rows <= 0) return cudaSuccess;
-  const int grid = (rows + 63) / 64;
-  auto yb = static_cast<__nv_bfloat16*>(y);
-  auto ytb = static_cast<__nv_bfloat16*>(y_t);
-  if (src_dtype == 0)
-    cast_bf16_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), yb, ytb, rows, d, ld_t, normalize);
-  else if (src_dtype == 1)
-    cast_bf16_kernel<__nv_bfloat16>
-        <<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), yb, ytb, rows, d, ld_t, normalize);
-  else
-    cast_bf16_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), yb, ytb, rows, d, ld_t, normalize);
+template <typename T>
+static cudaError_t launch_cast_t(const void* x0, void* y0, const void* x1, void* y1, int rows, int d, int normalize,
+                                 const float* logit_scale, float cap, float* scalars, cudaStream_t stream) {
+  auto a0 = static_cast<const T*>(x0), a1 = static_cast<const T*>(x1);
+  auto b0 = static_cast<__nv_bfloat16*>(y0), b1 = static_cast<__nv_bfloat16*>(y1);
+  if (normalize) {
+    normalize_cast_bf16_kernel<T><<<(rows + 7) / 8, 256, 0, stream>>>(a0, b0, rows, d);
+    return cudaGetLastError();
+  }
+  const size_t n_oct = static_cast<size_t>(rows) * d / 8;
+  size_t blocks = (n_oct + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  cast_bf16_kernel<T><<<dim3(static_cast<unsigned>(blocks), x1 != nullptr ? 2 : 1), 256, 0, stream>>>(
+      a0, b0, a1, b1, n_oct, logit_scale, cap, scalars);
   return cudaGetLastError();
+}
+
+static cudaError_t launch_cast_any(const void* x0, void* y0, const void* x1, void* y1, int src_dtype, int rows, int d,
+                                   int normalize, const float* logit_scale, float cap, float* scalars,
+                                   cudaStream_t stream) {
+  if (src_dtype == 0)
+    return launch_cast_t<float>(x0, y0, x1, y1, rows, d, normalize, logit_scale, cap, scalars, stream);
+  if (src_dtype == 1)
+    return launch_cast_t<__nv_bfloat16>(x0, y0, x1, y1, rows, d, normalize, logit_scale, cap, scalars, stream);
+  return launch_cast_t<__half>(x0, y0, x1, y1, rows, d, normalize, logit_scale, cap, scalars, stream);
+}
+
+cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, int rows, int d, int normalize,
+                             cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  return launch_cast_any(x, y, nullptr, nullptr, src_dtype, rows, d, normalize, nullptr, 0.f, nullptr, stream);
+}
+// cap + casts of both modalities: one launch
+cudaError_t launch_prepare(const void* image, const void* text, int src_dtype, int rows, int d, void* image_bf16,
+                           void* text_bf16, const float* logit_scale, float cap, float* scalars, cudaStream_t stream) {
+  return launch_cast_any(image, image_bf16, text, text_bf16, src_dtype, rows, d, 0, logit_scale, cap, scalars, stream);
 }
 
 // scalars[0] = s_eff = min(s, cap)  (forward value of the straight-through cap, losses.py:73-76)
@@ -289,59 +283,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float dot_bf16_row(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                              int d, int lane) {
-  float acc = 0.f;
-  for (int c = lane * 2; c < d; c += 64) {
-    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + c));
-    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + c));
-    acc = fmaf(fa.x, fb.x, acc);
-    acc = fmaf(fa.y, fb.y, acc);
-  }
-  return warp_sum(acc);
-}
 // warp per local row: stats = {L2 = m + log2(S0)  (LSE in log2 units), mu = S1/S0, var = S2/S0 - mu^2,
 //                              zq = sum_k q_k <x_i, y_col_k>}
-__global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restrict__ partial, int n_slots, int m_pad,
-                                                           int m_rows, int d, const __nv_bfloat16* __restrict__ x_rows,
-                                                           const __nv_bfloat16* __restrict__ y_all,
-                                                           const int* __restrict__ pos_col,
-                                                           const float* __restrict__ pos_q, int kp1,
-                                                           float4* __restrict__ row_stats) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= m_rows) return;
-  // lanes split the slots; the merge is a max-rescaled sum, combined across lanes in a fixed butterfly order
-  float m = -INFINITY;
-  for (int s = lane; s < n_slots; s += 32) m = fmaxf(m, partial[static_cast<size_t>(s) * m_pad + row].x);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  for (int s = lane; s < n_slots; s += 32) {
-    const float4 p = partial[static_cast<size_t>(s) * m_pad + row];
-    const float w = (p.x == -INFINITY) ? 0.f : exp2f(p.x - m);
-    s0 = fmaf(p.y, w, s0);
-    s1 = fmaf(p.z, w, s1);
-    s2 = fmaf(p.w, w, s2);
-  }
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  const float mu = s1 / s0;
-  const float var = s2 / s0 - mu * mu;
-  float zq = 0.f;
-  for (int t = 0; t < kp1; ++t) {
-    const int c = pos_col[static_cast<size_t>(row) * kp1 + t];
-    if (c < 0) continue;  // warp-uniform
-    const float z = dot_bf16_row(x_rows + static_cast<size_t>(row) * d, y_all + static_cast<size_t>(c) * d, d, lane);
-    zq = fmaf(pos_q[static_cast<size_t>(row) * kp1 + t], z, zq);
-  }
-  if (lane == 0) row_stats[row] = make_float4(m + log2f(s0), mu, var, zq);
-}
-// Developer variant (SCL_AUX_V2=1; the kernel above measured 24 % of the copy bandwidth, profiles/r1_hbm_passes.md,
-// because every dot product walks its two 1 KB rows in eight dependent 4-byte steps per lane): the same contract
-// with 16-byte loads, all loads of a dot product in flight together and the slot list of the row read once.
-// Summation order inside a dot product differs from the kernel above (last-bit differences in zq).
+// 16-byte loads, all loads of a dot product in flight together, the slot list of the row read once (lane t = slot t).
 __device__ __forceinline__ float dot8(const uint4& ua, const uint4& ub, float acc) {
   const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
   const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
@@ -354,7 +298,7 @@ __device__ __forceinline__ float dot8(const uint4& ua, const uint4& ub, float ac
   }
   return acc;
 }
-__global__ void __launch_bounds__(256) row_finalize_v2_kernel(const float4* __restrict__ partial, int n_slots,
+__global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restrict__ partial, int n_slots,
                                                               int m_pad, int m_rows, int d,
                                                               const __nv_bfloat16* __restrict__ x_rows,
                                                               const __nv_bfloat16* __restrict__ y_all,
@@ -417,24 +361,10 @@ __global__ void __launch_bounds__(256) row_finalize_v2_kernel(const float4* __re
   }
   if (lane == 0) row_stats[row] = make_float4(m + log2f(s0), mu, var, zq);
 }
-static bool aux_v2() {
-  static const bool on = [] {
-    const char* e = std::getenv("SCL_AUX_V2");
-    return e != nullptr && e[0] == '1' && e[1] == 0;
-  }();
-  return on;
-}
-
 cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, int m_rows, int d, const void* x_rows,
                                 const void* y_all, const int32_t* pos_col, const float* pos_q, int kp1,
                                 float4* row_stats, cudaStream_t stream) {
-  if (aux_v2() && kp1 <= 32 && d % 8 == 0) {
-    row_finalize_v2_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(partial, n_slots, m_pad, m_rows, d,
-                                                                 static_cast<const __nv_bfloat16*>(x_rows),
-                                                                 static_cast<const __nv_bfloat16*>(y_all), pos_col,
-                                                                 pos_q, kp1, row_stats);
-    return cudaGetLastError();
-  }
+  if (kp1 > 32) return cudaErrorInvalidValue;
   row_finalize_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(partial, n_slots, m_pad, m_rows, d,
                                                             static_cast<const __nv_bfloat16*>(x_rows),
                                                             static_cast<const __nv_bfloat16*>(y_all), pos_col, pos_q,
@@ -442,55 +372,68 @@ cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, i
   return cudaGetLastError();
 }
 
-// single CTA, fixed-order tree: sums6 = { sum_A (LSE - s_eff zq), sum_B (...), sum_A (mu - zq), sum_B (...),
-//                                         sum_A var, sum_B var }
-__global__ void __launch_bounds__(512) reduce_rows_kernel(const float4* __restrict__ stats_a,
-                                                           const float4* __restrict__ stats_b, int m_rows,
-                                                           const float* __restrict__ scalars,
-                                                           float* __restrict__ sums6) {
-  __shared__ double sh[6][512];
-  const float s_eff = scalars[0];
+// sums6 = { sum_A (LSE - s_eff zq), sum_B (...), sum_A (mu - zq), sum_B (...), sum_A var, sum_B var }
+// Single CTA, fixed-order fp64 tree (deterministic); 1024 threads with four independent row loads in flight each.
+// When out4 != nullptr the loss scalars (scl_loss_scalars) are evaluated by the same launch.
+__device__ __forceinline__ void loss_scalars_from(const float* sums6, float c, float w, float* out4) {
+  const float gsum = c * (sums6[2] + sums6[3]);
+  const float gap = w > 0.f ? gsum : 0.f;
+  out4[0] = c * (sums6[0] + sums6[1]) + w * gap * gap;
+  out4[1] = gap;
+  out4[2] = gsum + 2.f * w * gap * c * (sums6[4] + sums6[5]);
+  out4[3] = 2.f * w * gap;
+}
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float4* __restrict__ stats_a,
+                                                            const float4* __restrict__ stats_b, int m_rows,
+                                                            const float* __restrict__ scalars,
+                                                            float* __restrict__ sums6, float c, float w,
+                                                            float* __restrict__ out4) {
+  __shared__ double sh[6][1024];
+  const double s_eff = scalars[0];
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < m_rows; i += 512) {
-    const float4 a = stats_a[i];
-    const float4 b = stats_b[i];
-    acc[0] += static_cast<double>(a.x) * kLn2 - static_cast<double>(s_eff) * a.w;
-    acc[1] += static_cast<double>(b.x) * kLn2 - static_cast<double>(s_eff) * b.w;
-    acc[2] += static_cast<double>(a.y) - a.w;
-    acc[3] += static_cast<double>(b.y) - b.w;
-    acc[4] += a.z;
-    acc[5] += b.z;
+  for (int i0 = threadIdx.x; i0 < m_rows; i0 += 4096) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 1024;
+      a[u] = i < m_rows ? stats_a[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      b[u] = i < m_rows ? stats_b[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[0] += static_cast<double>(a[u].x) * kLn2 - s_eff * a[u].w;
+      acc[1] += static_cast<double>(b[u].x) * kLn2 - s_eff * b[u].w;
+      acc[2] += static_cast<double>(a[u].y) - a[u].w;
+      acc[3] += static_cast<double>(b[u].y) - b[u].w;
+      acc[4] += a[u].z;
+      acc[5] += b[u].z;
+    }
   }
   for (int k = 0; k < 6; ++k) sh[k][threadIdx.x] = acc[k];
   __syncthreads();
-  for (int o = 256; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o)
       for (int k = 0; k < 6; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
     __syncthreads();
   }
   if (threadIdx.x < 6) sums6[threadIdx.x] = static_cast<float>(sh[threadIdx.x][0]);
+  __syncthreads();
+  if (threadIdx.x == 0 && out4 != nullptr) loss_scalars_from(sums6, c, w, out4);
 }
 cudaError_t launch_reduce_rows(const float4* stats_a, const float4* stats_b, int m_rows, const float* scalars,
-                               float* sums6, cudaStream_t stream) {
-  reduce_rows_kernel<<<1, 512, 0, stream>>>(stats_a, stats_b, m_rows, scalars, sums6);
+                               float* sums6, float c, float w, float* out4, cudaStream_t stream) {
+  reduce_rows_kernel<<<1, 1024, 0, stream>>>(stats_a, stats_b, m_rows, scalars, sums6, c, w, out4);
   return cudaGetLastError();
 }
 
 // out4 = { loss, gap, d loss / d logit_scale, 2*w*gap }   (losses.py:113-122; SURVEY §8a closed forms)
-__global__ void loss_scalars_kernel(const float* __restrict__ sums6, const float* __restrict__ scalars, float c,
-                                    float w, float* __restrict__ out4) {
-  const float gsum = c * (sums6[2] + sums6[3]);
-  const float gap = w > 0.f ? gsum : 0.f;
-  const float loss = c * (sums6[0] + sums6[1]) + w * gap * gap;
-  const float ds = gsum + 2.f * w * gap * c * (sums6[4] + sums6[5]);
-  out4[0] = loss;
-  out4[1] = gap;
-  out4[2] = ds;
-  out4[3] = 2.f * w * gap;
+__global__ void loss_scalars_kernel(const float* __restrict__ sums6, float c, float w, float* __restrict__ out4) {
+  loss_scalars_from(sums6, c, w, out4);
 }
 cudaError_t launch_loss_scalars(const float* sums6, const float* scalars, float c, float w, float* out4,
                                 cudaStream_t stream) {
-  loss_scalars_kernel<<<1, 1, 0, stream>>>(sums6, scalars, c, w, out4);
+  (void)scalars;
+  loss_scalars_kernel<<<1, 1, 0, stream>>>(sums6, c, w, out4);
   return cudaGetLastError();
 }
 
@@ -548,24 +491,126 @@ cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, co
 }
 
 // =====================================================================================
-// backward finish: chunk partial sums + sparse soft-target terms + cast
+// backward finish: chunk partial sums + sparse soft-target terms + cast  (deterministic: no atomics on dX)
 // =====================================================================================
-// warp per local row:  dx32[i,:] = sum_chunks partial  -  g*c*(s_eff + k2_rank) * sum_{k>=1} q_ik * Y[col_ik,:]
+// Reverse lists: the gathered opposite-direction soft-target lists name, per entry e = (row j, slot t >= 1), a column
+// cc; the entries whose column is one of OUR rows (rank*B_l <= cc < (rank+1)*B_l) contribute
+//   dX[cc - rank*B_l, :] -= g*c*(s_eff + k2_owner(j)) * q_jt * Y[j, :].
+// They are bucketed per local row (count -> exclusive scan -> fill; the fill order inside a bucket is arbitrary) and
+// the consumer visits every bucket in ascending e, so the fp32 summation order is fixed from run to run.
+__device__ __forceinline__ bool rev_entry_hits(long long e, int kp1, int b_local, int rank, int col_mode, int cc) {
+  const int j = static_cast<int>(e / kp1);
+  const int t = static_cast<int>(e - static_cast<long long>(j) * kp1);
+  const bool mode_ok = col_mode == 2 || (col_mode == 1 && j / b_local == rank);
+  return t != 0 && mode_ok && cc >= rank * b_local && cc < (rank + 1) * b_local;  // slot 0: inside the tensor-core kernel
+}
+__global__ void __launch_bounds__(256) rev_count_kernel(const int* __restrict__ opp_col_all, long long total, int kp1,
+                                                        int b_local, int rank, int col_mode, int* __restrict__ cnt) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int cc = opp_col_all[e];
+  if (rev_entry_hits(e, kp1, b_local, rank, col_mode, cc)) atomicAdd(&cnt[cc - rank * b_local], 1);
+}
+// single CTA: off[i] = sum_{i' < i} cnt[i'], off[n] = total; cursor[i] = off[i]
+__global__ void __launch_bounds__(1024) rev_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ off,
+                                                        int* __restrict__ cursor) {
+  __shared__ int sh[1024];
+  const int per = (n + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(n, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += cnt[i];
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = sh[threadIdx.x] - sum;
+  for (int i = lo; i < hi; ++i) {
+    off[i] = run;
+    cursor[i] = run;
+    run += cnt[i];
+  }
+  if (threadIdx.x == 1023) off[n] = sh[1023];
+}
+__global__ void __launch_bounds__(256) rev_fill_kernel(const int* __restrict__ opp_col_all, long long total, int kp1,
+                                                       int b_local, int rank, int col_mode, int* __restrict__ cursor,
+                                                       int* __restrict__ list) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int cc = opp_col_all[e];
+  if (rev_entry_hits(e, kp1, b_local, rank, col_mode, cc))
+    list[atomicAdd(&cursor[cc - rank * b_local], 1)] = static_cast<int>(e);
+}
+size_t bwd_finish_workspace_bytes(int n_global, int b_local, int kp1) {
+  // cnt[b_local] | off[b_local + 1] | cursor[b_local] | list[n_global * kp1]
+  return (static_cast<size_t>(3) * b_local + 1 + static_cast<size_t>(n_global) * kp1) * sizeof(int) + 256;
+}
+
+__device__ __forceinline__ void fma_row4(float4& acc, float qc, const __nv_bfloat16* __restrict__ yrow, int c0, int y_lo) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(yrow + c0);
+  float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  if (y_lo >= 0) {  // fp32-accurate mode: add the low-order bf16 part of the row
+    const uint2 raw2 = *reinterpret_cast<const uint2*>(yrow + y_lo + c0);
+    const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.x));
+    const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.y));
+    lo.x += lo2.x; lo.y += lo2.y; hi.x += hi2.x; hi.y += hi2.y;
+  }
+  acc.x = fmaf(qc, lo.x, acc.x); acc.y = fmaf(qc, lo.y, acc.y);
+  acc.z = fmaf(qc, hi.x, acc.z); acc.w = fmaf(qc, hi.y, acc.w);
+}
+// warp per local row:
+//   dX[i,:] = sum_chunks partial                                            (chunk order)
+//           - g*c*(s_eff + k2_rank) * sum_{k>=1} q_ik * Y[col_ik,:]           (slot order)
+//           - sum over the row's reverse bucket, ascending e                  (see above)
+// written as fp32 (OutT = float) or cast on the way out.  y_ld: row pitch of y_all in elements; y_lo >= 0
+// (fp32-accurate mode): offset of the low-order bf16 part of every row.
+template <typename OutT>
 __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
                                                          int m_rows, int d, const __nv_bfloat16* __restrict__ y_all,
                                                          const int* __restrict__ pos_col,
-                                                         const float* __restrict__ pos_q, int kp1, int rank,
+                                                         const float* __restrict__ pos_q, int kp1, int b_local, int rank,
                                                          const float* __restrict__ gaps,
                                                          const float* __restrict__ scalars,
                                                          const float* __restrict__ grad_out, float c, float w,
                                                          float mult, int y_ld, int y_lo,
-                                                         float* __restrict__ dx32) {
-  // y_ld: row pitch of y_all in elements; y_lo >= 0 (fp32-accurate mode): offset of the low-order bf16 part of
-  // every row, added to the high-order part
+                                                         const int* __restrict__ rev_off, const int* __restrict__ rev_list,
+                                                         const float* __restrict__ opp_q_all,
+                                                         OutT* __restrict__ dx_out) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= m_rows) return;
-  const float coef = grad_out[0] * mult * c * (scalars[0] + 2.f * w * gaps[rank]);
+  const float base = grad_out[0] * mult * c;
+  const float s_eff = scalars[0];
+  const float coef = base * (s_eff + 2.f * w * gaps[rank]);
+  // own list: lane t holds slot t
+  int my_col = -1;
+  float my_qc = 0.f;
+  if (lane >= 1 && lane < kp1) {
+    my_col = pos_col[static_cast<size_t>(row) * kp1 + lane];
+    my_qc = -coef * pos_q[static_cast<size_t>(row) * kp1 + lane];
+  }
+  const unsigned own_mask = __ballot_sync(0xffffffffu, my_col >= 0);
+  const int r_lo = rev_off != nullptr ? rev_off[row] : 0;
+  const int r_n = rev_off != nullptr ? rev_off[row + 1] - r_lo : 0;
+  // the common case (bucket of <= 32 entries): order it once, lane p keeps the p-th smallest entry
+  int s_j = 0;
+  float s_qc = 0.f;
+  if (r_n > 0 && r_n <= 32) {
+    const unsigned mine0 = lane < r_n ? static_cast<unsigned>(rev_list[r_lo + lane]) : 0xffffffffu;
+    unsigned mine = mine0;
+    for (int p = 0; p < r_n; ++p) {
+      const unsigned e = __reduce_min_sync(0xffffffffu, mine);
+      if (mine == e) mine = 0xffffffffu;  // entries are unique
+      if (lane == p) {
+        s_j = static_cast<int>(e) / kp1;
+        s_qc = -base * (s_eff + 2.f * w * gaps[s_j / b_local]) * opp_q_all[e];
+      }
+    }
+  }
   for (int c0 = lane * 4; c0 < d; c0 += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ch = 0; ch < chunks; ++ch) {
@@ -573,85 +618,47 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
           *reinterpret_cast<const float4*>(dx_partial + (static_cast<size_t>(ch) * m_pad + row) * d + c0);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
-    for (int t = 1; t < kp1; ++t) {  // slot 0 (own column) is handled inside bwd_rows_kernel
-      const int col = pos_col[static_cast<size_t>(row) * kp1 + t];
-      if (col < 0) continue;
-      const float qc = -coef * pos_q[static_cast<size_t>(row) * kp1 + t];
-      const uint2 raw = *reinterpret_cast<const uint2*>(y_all + static_cast<size_t>(col) * y_ld + c0);
-      float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-      if (y_lo >= 0) {
-        const uint2 raw2 = *reinterpret_cast<const uint2*>(y_all + static_cast<size_t>(col) * y_ld + y_lo + c0);
-        const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.x));
-        const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw2.y));
-        lo.x += lo2.x; lo.y += lo2.y; hi.x += hi2.x; hi.y += hi2.y;
+    for (unsigned m = own_mask; m; m &= m - 1) {
+      const int t = __ffs(m) - 1;
+      const int col = __shfl_sync(0xffffffffu, my_col, t);
+      const float qc = __shfl_sync(0xffffffffu, my_qc, t);
+      fma_row4(acc, qc, y_all + static_cast<size_t>(col) * y_ld, c0, y_lo);
+    }
+    if (r_n <= 32) {
+      for (int p = 0; p < r_n; ++p) {
+        const int j = __shfl_sync(0xffffffffu, s_j, p);
+        const float qc = __shfl_sync(0xffffffffu, s_qc, p);
+        fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
       }
-      acc.x = fmaf(qc, lo.x, acc.x); acc.y = fmaf(qc, lo.y, acc.y);
-      acc.z = fmaf(qc, hi.x, acc.z); acc.w = fmaf(qc, hi.y, acc.w);
     }
-    *reinterpret_cast<float4*>(dx32 + static_cast<size_t>(row) * d + c0) = acc;
-  }
-}
-// Scan of the gathered opposite-direction lists: lane = one (row j, slot t) entry (coalesced), entries that
-// list one of OUR rows as a positive are then processed by the whole warp, one hit at a time:
-//   dx32[col - rank*B_l, :] -= g*c*(s_eff + k2_owner(j)) * q_jt * Y[j,:]        (fp32 atomics)
-__global__ void __launch_bounds__(256) bwd_scatter_kernel(const int* __restrict__ opp_col_all,
-                                                          const float* __restrict__ opp_q_all, int n_global, int kp1,
-                                                          int b_local, int rank, int d,
-                                                          const __nv_bfloat16* __restrict__ y_all,
-                                                          const float* __restrict__ gaps,
-                                                          const float* __restrict__ scalars,
-                                                          const float* __restrict__ grad_out, float c, float w,
-                                                          float mult, int col_mode, int y_ld, int y_lo,
-                                                          float* __restrict__ dx32) {
-  const int lane = threadIdx.x & 31;
-  const long long total = static_cast<long long>(n_global) * kp1;
-  const long long e = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 32 + lane;
-  int col = -1, j = 0;
-  float qv = 0.f;
-  if (e < total) {
-    j = static_cast<int>(e / kp1);
-    const int t = static_cast<int>(e - static_cast<long long>(j) * kp1);
-    const int cc = opp_col_all[e];
-    const int owner = j / b_local;
-    const bool mode_ok = col_mode == 2 || (col_mode == 1 && owner == rank);
-    // slot 0 (own column) is handled inside the tensor-core kernel
-    if (t != 0 && mode_ok && cc >= rank * b_local && cc < (rank + 1) * b_local) {
-      col = cc;
-      qv = opp_q_all[e];
-    }
-  }
-  unsigned hits = __ballot_sync(0xffffffffu, col >= 0);
-  const float base = -grad_out[0] * mult * c;
-  const float s_eff = scalars[0];
-  while (hits) {
-    const int src = __ffs(hits) - 1;
-    hits &= hits - 1;
-    const int hc = __shfl_sync(0xffffffffu, col, src);
-    const int hj = __shfl_sync(0xffffffffu, j, src);
-    const float hq = __shfl_sync(0xffffffffu, qv, src);
-    const float qc = base * (s_eff + 2.f * w * gaps[hj / b_local]) * hq;
-    float* dst = dx32 + static_cast<size_t>(hc - rank * b_local) * d;
-    const __nv_bfloat16* yrow = y_all + static_cast<size_t>(hj) * y_ld;
-    for (int c0 = lane * 2; c0 < d; c0 += 64) {
-      float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + c0));
-      if (y_lo >= 0) {
-        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yrow + y_lo + c0));
-        v.x += v2.x;
-        v.y += v2.y;
+    // larger buckets (hub rows): ascending entry order by repeated warp-wide selection of the smallest entry > last
+    int last = -1;
+    for (int done = 0; r_n > 32 && done < r_n; ++done) {
+      unsigned mine = 0xffffffffu;
+      for (int k = lane; k < r_n; k += 32) {
+        const int e = rev_list[r_lo + k];
+        if (e > last) mine = min(mine, static_cast<unsigned>(e));
       }
-      atomicAdd(dst + c0, qc * v.x);
-      atomicAdd(dst + c0 + 1, qc * v.y);
+      const int e = static_cast<int>(__reduce_min_sync(0xffffffffu, mine));
+      last = e;
+      const int j = e / kp1;
+      const float qc = -base * (s_eff + 2.f * w * gaps[j / b_local]) * opp_q_all[e];
+      fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
     }
-  }
-}
-template <typename T>
-__global__ void cast_out_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) {
-    if constexpr (sizeof(T) == 2) {
-      if constexpr (std::is_same<T, __nv_bfloat16>::value) dst[i] = __float2bfloat16_rn(src[i]);
-      else dst[i] = __float2half_rn(src[i]);
+    if constexpr (std::is_same<OutT, float>::value) {
+      *reinterpret_cast<float4*>(dx_out + static_cast<size_t>(row) * d + c0) = acc;
+    } else if constexpr (std::is_same<OutT, __nv_bfloat16>::value) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dx_out + static_cast<size_t>(row) * d + c0) = pk;
+    } else {
+      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dx_out + static_cast<size_t>(row) * d + c0) = pk;
     }
   }
 }
@@ -660,28 +667,79 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                               const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
                               const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                               const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
-                              int split, float* dx32, void* dx_out, int out_dtype, cudaStream_t stream) {
+                              int split, void* workspace, size_t workspace_bytes, void* dx_out, int out_dtype,
+                              cudaStream_t stream) {
+  if (kp1 > 32) return cudaErrorInvalidValue;
   auto yb = static_cast<const __nv_bfloat16*>(y_all);
   const int y_ld = split ? 3 * d : d;  // split: y_all is the (h | l | h) column operand
   const int y_lo = split ? d : -1;
-  bwd_gather_kernel<<<(m_rows + 7) / 8, 256, 0, stream>>>(dx_partial, chunks, m_pad, m_rows, d, yb, pos_col, pos_q,
-                                                          kp1, rank, gaps, scalars, grad_out, c, w, mult, y_ld, y_lo,
-                                                          dx32);
+  const int* rev_off = nullptr;
+  const int* rev_list = nullptr;
   if (col_mode != 0) {
-    const long long entries = static_cast<long long>(n_global) * kp1;
-    bwd_scatter_kernel<<<static_cast<unsigned>((entries + 255) / 256), 256, 0, stream>>>(
-        opp_col_all, opp_q_all, n_global, kp1, b_local, rank, d, yb, gaps, scalars, grad_out, c, w, mult, col_mode,
-        y_ld, y_lo, dx32);
+    if (workspace == nullptr || workspace_bytes < bwd_finish_workspace_bytes(n_global, b_local, kp1))
+      return cudaErrorInvalidValue;
+    int* cnt = static_cast<int*>(workspace);
+    int* off = cnt + b_local;
+    int* cursor = off + b_local + 1;
+    int* list = cursor + b_local;
+    const long long total = static_cast<long long>(n_global) * kp1;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(b_local) * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    rev_count_kernel<<<blocks, 256, 0, stream>>>(opp_col_all, total, kp1, b_local, rank, col_mode, cnt);
+    rev_scan_kernel<<<1, 1024, 0, stream>>>(cnt, b_local, off, cursor);
+    rev_fill_kernel<<<blocks, 256, 0, stream>>>(opp_col_all, total, kp1, b_local, rank, col_mode, cursor, list);
+    rev_off = off;
+    rev_list = list;
   }
-  const size_t n = static_cast<size_t>(m_rows) * d;
-  if (out_dtype == 1)
-    cast_out_kernel<__nv_bfloat16><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-        dx32, static_cast<__nv_bfloat16*>(dx_out), n);
-  else if (out_dtype == 2)
-    cast_out_kernel<__half><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(dx32, static_cast<__half*>(dx_out), n);
+  const unsigned grid = (m_rows + 7) / 8;
+#define SCL_GATHER(T)                                                                                                 \
+  bwd_gather_kernel<T><<<grid, 256, 0, stream>>>(dx_partial, chunks, m_pad, m_rows, d, yb, pos_col, pos_q, kp1,       \
+                                                 b_local, rank, gaps, scalars, grad_out, c, w, mult, y_ld, y_lo,      \
+                                                 rev_off, rev_list, opp_q_all, static_cast<T*>(dx_out))
+  if (out_dtype == 0) SCL_GATHER(float);
+  else if (out_dtype == 1) SCL_GATHER(__nv_bfloat16);
+  else SCL_GATHER(__half);
+#undef SCL_GATHER
   return cudaGetLastError();
 }
 
+// =====================================================================================
+// caller-resolved soft targets (SpatialLossFromColumns): validate and sanitise
+// =====================================================================================
+// The kernels index y_all + col * d for every col >= 0 and assume slot 0 is the row's own column.  Lists that come
+// from outside the library are therefore copied through this pass: out-of-range columns become unused slots
+// (flag bit 0), unused slots get q = 0 (bit 2 when they carried weight), a slot 0 other than rank*B_l + i sets bit 1.
+__global__ void __launch_bounds__(256) check_positives_kernel(const int* __restrict__ col_in,
+                                                              const float* __restrict__ q_in, int b_local, int kp1,
+                                                              int n_global, int rank, int* __restrict__ col_out,
+                                                              float* __restrict__ q_out, int* __restrict__ flag) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= b_local * kp1) return;
+  const int i = idx / kp1, t = idx - i * kp1;
+  int c = col_in[idx];
+  float q = q_in[idx];
+  int bits = 0;
+  if (c < -1 || c >= n_global) {
+    bits |= 1;
+    c = -1;
+  }
+  if (t == 0 && c != rank * b_local + i) bits |= 2;
+  if (c < 0 && q != 0.f) {
+    if (col_in[idx] == -1) bits |= 4;
+    q = 0.f;
+  }
+  col_out[idx] = c;
+  q_out[idx] = q;
+  if (bits) atomicOr(flag, bits);
+}
+cudaError_t launch_check_positives(const int32_t* col_in, const float* q_in, int b_local, int kp1, int n_global,
+                                   int rank, int32_t* col_out, float* q_out, int* flag, cudaStream_t stream) {
+  const int n = b_local * kp1;
+  check_positives_kernel<<<(n + 255) / 256, 256, 0, stream>>>(col_in, q_in, b_local, kp1, n_global, rank, col_out,
+                                                              q_out, flag);
+  return cudaGetLastError();
+}
 
 // =====================================================================================
 // statistics exchange: split the all-gathered per-rank records back into contiguous arrays

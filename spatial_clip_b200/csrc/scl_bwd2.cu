@@ -1,22 +1,23 @@
-// Backward row-gradient kernel, CTA-pair version (tcgen05 cta_group::2, cluster of 2 CTAs).
+// Backward row-gradient kernel (tcgen05 cta_group::2, cluster of 2 CTAs).
 //
-// Same contract as bwd_rows_kernel (scl_bwd.cu):  dX[i,:] = sum_j G_ij Y[j,:],
+//   dX[i,:] = sum_j G_ij Y[j,:],
 //   G_ij = P_ij (u_i + v_i z_ij) + Pc_ij (u'_j + v'_j z_ij) - [j == own column] t_i,
-// but organised so that the similarity tile is recomputed exactly ONCE per (row block, column tile):
+// organised so that the similarity tile is recomputed exactly ONCE per (row block, column tile):
 // a CTA pair owns 128 rows (64 per CTA).  With UMMA M = 128 across two SMs each SM keeps a 64-row slice
 // of every accumulator in the "2x2" TMEM layout (64 rows x N as 128 lanes x N/2 columns: lanes 64..127
 // hold the upper half of N), so per SM
 //   dX accumulator  [64 x 512] fp32 = 2 groups x 128 columns     (TMEM columns   0..255)
 //   z tile          [64 x 256] fp32 =            128 columns x 2 (TMEM columns 256..511, double buffered)
-// fit together -- which a single SM with 128 rows cannot do at D = 512 (the single-CTA kernel splits D
-// and recomputes z twice).  G is written once per CTA ([64 x 256] bf16) and both GEMMs are issued by
-// the leader CTA's MMA thread with cta_group::2.
+// fit together.  G is written once per CTA ([64 x 256] bf16) and both GEMMs are issued by the leader CTA's MMA
+// thread with cta_group::2.
 //
-// Barriers (same smem offset in both CTAs): x_full, full[s], tmem_empty[b], g_full[b] are waited on by
+// The gradient GEMM reads Y itself as an MN-major B operand: tm_cols_mn is a {64 d, 64 j}-box map over the row-major
+// Y [N, D] (the same bytes as tm_cols, a different box), whose SWIZZLE_128B image is exactly the canonical MN-major
+// UMMA layout (umma_desc_mnmajor_sw128) -- no transposed copy of Y exists anywhere.
+//
+// Barriers (same smem offset in both CTAs): x_full, full[s], tmem_empty[b], g_full are waited on by
 // the leader (TMA bytes / remote arrivals from the peer are credited to the leader's copy); empty[s],
-// tmem_full[b], g_empty[b], acc_full are multicast by the leader's tcgen05.commit to both CTAs.
-#include <cstdlib>
-
+// tmem_full[b], g_empty, acc_full are multicast by the leader's tcgen05.commit to both CTAs.
 #include "scl_kernels.h"
 #include "scl_ptx.cuh"
 
@@ -25,7 +26,10 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-constexpr int kB2Stages = 3;            // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
+#ifndef SCL_B2_STAGES
+#define SCL_B2_STAGES 3
+#endif
+constexpr int kB2Stages = SCL_B2_STAGES;  // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
 constexpr int kB2SlotBytes = 16384;
 constexpr int kB2StageBytes = 2 * kB2SlotBytes;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
@@ -57,31 +61,20 @@ struct B2Bars {
   uint32_t tmem_base;
 };
 
-// kTune (developer knob SCL_BWD_TUNE, default 0; see profiles/r1_smem_port_accounting.md):
-//   bit 0: column coefficients / G tile through explicit shared-window LDS.128 / STS.128
-//   bit 1: epilogue barrier waits park with a suspend-time hint instead of re-polling every ~100 cycles
-//   bit 2: the same for the TMA-producer and MMA-issuer waits
 // kSplit = 1 is the fp32-accurate ("bf16x2") mode: every operand is a bf16 hi + lo pair.  The similarity is
 // contracted over the K-concatenated rows X' = (h|h|l), Y' = (h|l|h) of width 3 d (x.y ~= xh.yh + xh.yl + xl.yh,
 // the dropped terms are O(2^-18)), G is written as two bf16 tiles G1 + G2 and the gradient GEMM runs three passes
-// G1.Yh + G1.Yl + G2.Yh against the stacked transposed copy [Yh^T ; Yl^T] ([2 d, ld]).  X is always streamed.
-// kMN = 1 (developer knob SCL_BWD_MN, not with kSplit): the gradient GEMM reads Y itself as an MN-major operand
-// (tm_cols_t is then a {64, 64}-box map over the row-major Y [N, D]); no transposed copy of Y exists at all.
-template <int kTune, int kSplit, int kMN>
+// G1.Yh + G1.Yl + G2.Yh, reading Yh / Yl as the column ranges [0, d) / [d, 2 d) of Y'.  X is always streamed.
+template <int kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kB2Threads, 1)
-bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, D]  box {64, 64}
-                     const __grid_constant__ CUtensorMap tm_cols,    // Y   [N, D]  box {64, 128}
-                     const __grid_constant__ CUtensorMap tm_cols_t,  // Y^T [D, N]  box {64, 128}
+bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, kd]  box {64, 64}
+                     const __grid_constant__ CUtensorMap tm_cols,     // Y [N, kd]  box {64, 128}
+                     const __grid_constant__ CUtensorMap tm_cols_mn,  // Y [N, kd]  box {64, 64}
                      int m_rows, int n_cols, int d, int d_slices, int n_tiles, int tiles_per_chunk, int m_pad,
                      int diag0, const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
-                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial,
-                     long long* __restrict__ dbg_t) {
+                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ B2Bars bars;
-  const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
-  long long* my_t = timed ? dbg_t + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16
-                          : nullptr;
-  const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = (kSplit ? 3 * d : d) / kB2BK;  // K chunks of the similarity contraction
   // D <= 512: one D slice, X block resident.  D > 512 (TMEM cannot hold dX[64 x D]): blockIdx.z selects a
@@ -93,7 +86,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary (absent when streamed)
   uint8_t* smem_g = smem_x + (stream_x ? 0 : nk * kB2XChunkBytes);  // 32 KB, single buffer
   uint8_t* smem_g2 = smem_g + kB2GBytes;                 // split mode only: the low-order tile G2
-  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // 3 x 32 KB
+  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // kB2Stages x 32 KB
   uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (ds + 255) / 256;  // accumulator groups of up to 256 output columns
@@ -110,7 +103,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
   if (warp == kB2ProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_rows);
     tma_prefetch_desc(&tm_cols);
-    tma_prefetch_desc(&tm_cols_t);
+    tma_prefetch_desc(&tm_cols_mn);
     mbar_init(&bars.x_full, 1);
     for (int s = 0; s < kB2Stages; ++s) {
       mbar_init(&bars.full[s], 1);
@@ -146,12 +139,18 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       }
       int ring_s = 0;
       uint32_t ring_ph = 0;
-      long long w_empty = 0, w_ce = 0;
+#ifdef SCL_LAB_NO_TMA
+      int lab_loads = 0;  // lab: only the first round of the ring is really loaded
+#endif
       // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
       auto acquire = [&](int bytes_per_cta) {
         const int s = ring_s;
-        if constexpr ((kTune & 4) != 0) mbar_wait_hint(&bars.empty[s], ring_ph ^ 1, 2000u);
-        else mbar_wait_t(&bars.empty[s], ring_ph ^ 1, timed, w_empty);
+        mbar_wait(&bars.empty[s], ring_ph ^ 1);
+#ifdef SCL_LAB_NO_TMA
+        if (lab_loads >= kB2Stages) {
+          if (leader) mbar_arrive(&bars.full[s]);
+        } else
+#endif
         if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
         if (++ring_s == kB2Stages) {
           ring_s = 0;
@@ -159,11 +158,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
         return s;
       };
+#ifdef SCL_LAB_NO_TMA
+#define SCL_LAB_LOAD(...) do { if (lab_loads < kB2Stages) { __VA_ARGS__; } } while (0)
+#define SCL_LAB_STAGE_DONE() (++lab_loads)
+#else
+#define SCL_LAB_LOAD(...) do { __VA_ARGS__; } while (0)
+#define SCL_LAB_STAGE_DONE() ((void)0)
+#endif
       auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
         const int cb = lt & 1;
-        if constexpr ((kTune & 4) != 0) mbar_wait_hint(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, 2000u);
-        else mbar_wait_t(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1, timed, w_ce);
+        mbar_wait(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars.coef_full[cb], kB2CoefBytes);
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
@@ -171,53 +176,49 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         if (stream_x) {  // one K chunk per stage: Y chunk in slot 0, X chunk (8 KB) in slot 1
           for (int kc = 0; kc < nk; ++kc) {
             const int s = acquire(kB2SlotBytes + kB2XChunkBytes);
-            tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
-            tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK, row0);
+            SCL_LAB_LOAD(
+                tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+                tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK,
+                                 row0));
+            SCL_LAB_STAGE_DONE();
           }
         } else {
           for (int kc = 0; kc < nk; kc += 2) {
             const int nb = min(2, nk - kc);
             const int s = acquire(nb * kB2SlotBytes);
             for (int b = 0; b < nb; ++b)
-              tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
-                               (kc + b) * kB2BK, col0);
+              SCL_LAB_LOAD(tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
+                                            (kc + b) * kB2BK, col0));
+            SCL_LAB_STAGE_DONE();
           }
         }
       };
-      auto push_yt = [&](int lt) {
+      auto push_y = [&](int lt) {
         const int col0 = (t_begin + lt) * kB2TileN;
         const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
-        for (int p = 0; p < (kSplit ? 3 : 1); ++p) {  // split passes: (G1, Yh^T), (G1, Yl^T), (G2, Yh^T)
-          const int t_row0 = (p == 1) ? d : 0;        // Yl^T is stacked below Yh^T
+        for (int p = 0; p < (kSplit ? 3 : 1); ++p) {  // split passes: (G1, Yh), (G1, Yl), (G2, Yh)
+          const int p_d0 = (p == 1) ? d : 0;          // Yl sits at columns [d, 2 d) of Y' = (h | l | h)
           for (int u = 0; u < n_units; u += 2) {
             const int nb = min(2, n_units - u);
             const int s = acquire(nb * kB2SlotBytes);
             for (int b = 0; b < nb; ++b) {
               const int js = (u + b) / ng, g = (u + b) % ng;
               const int n_g = min(256, ds - 256 * g);
-              if constexpr (kMN != 0) {
-                // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
-                const int dbase = d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
-                uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
-                tma_load_2d_pair(slot, &tm_cols_t, &bars.full[s], dbase, col0 + js * 64);
-                tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_t, &bars.full[s], dbase + 64, col0 + js * 64);
-              } else {
-                tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols_t, &bars.full[s],
-                                 col0 + js * 64, t_row0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2));
-              }
+              // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
+              const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
+              uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
+              SCL_LAB_LOAD(
+                  tma_load_2d_pair(slot, &tm_cols_mn, &bars.full[s], dbase, col0 + js * 64);
+                  tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.full[s], dbase + 64, col0 + js * 64));
             }
+            SCL_LAB_STAGE_DONE();
           }
         }
       };
       push_z(0);
       for (int lt = 0; lt < n_my; ++lt) {
         if (lt + 1 < n_my) push_z(lt + 1);
-        push_yt(lt);
-      }
-      if (timed) {
-        my_t[0] = clock64() - t_start;
-        my_t[1] = w_empty;
-        my_t[2] = w_ce;
+        push_y(lt);
       }
     }
   } else if (warp == kB2MmaWarp) {
@@ -227,16 +228,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     // MMAs of 65 cycles per wait left the tensor pipe under-fed.
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
-      long long w_x = 0, w_te = 0, w_fz = 0, w_gf = 0, w_fy = 0;
-      auto mma_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
-        if constexpr ((kTune & 4) != 0) {
-          mbar_wait_hint(bar, parity, 1000u);
-          __syncwarp();
-        } else {
-          mbar_wait_warp(bar, parity, timed, acc);
-        }
-      };
-      if (!stream_x) mbar_wait_warp(&bars.x_full, 0, timed, w_x);
+      if (!stream_x) mbar_wait_warp(&bars.x_full, 0);
       tc_fence_after();
       int ring_s = 0;
       uint32_t ring_ph = 0;
@@ -248,14 +240,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       };
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
-        mma_wait(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, w_te);
+        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
         const int kstep = stream_x ? 1 : 2;
         for (int kc = 0; kc < nk; kc += kstep, advance()) {
           const int nb = min(kstep, nk - kc);
           const int s = ring_s;
-          mma_wait(&bars.full[s], ring_ph, w_fz);
+          mbar_wait_warp(&bars.full[s], ring_ph);
           tc_fence_after();
           if (elect_one()) {
             for (int b = 0; b < nb; ++b) {
@@ -274,7 +266,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         }
       };
       auto issue_acc = [&](int lt) {
-        mma_wait(&bars.g_full, lt & 1, w_gf);
+        mbar_wait_warp(&bars.g_full, lt & 1);
         tc_fence_after();
         const int n_units = 4 * ng;
         constexpr int n_pass = kSplit ? 3 : 1;
@@ -283,22 +275,19 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           for (int u = 0; u < n_units; u += 2, advance()) {
             const int nb = min(2, n_units - u);
             const int s = ring_s;
-            mma_wait(&bars.full[s], ring_ph, w_fy);
+            mbar_wait_warp(&bars.full[s], ring_ph);
             tc_fence_after();
             if (elect_one()) {
               for (int b = 0; b < nb; ++b) {
                 const int js = (u + b) / ng, g = (u + b) % ng;
-                const uint32_t idesc_acc =
-                    umma_idesc_bf16(128, min(256, ds - 256 * g)) | (kMN != 0 ? kUmmaIdescBMnMajor : 0u);
+                const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g)) | kUmmaIdescBMnMajor;
                 const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(g_tile + js * kB2GSubBytes));
-                const uint32_t b_addr = smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes);
-                // K-major Y^T box: +32 B per K = 16 step; MN-major Y boxes: 16 rows of 128 B = +2048 B per step
-                const uint64_t b_desc = kMN != 0 ? umma_desc_mnmajor_sw128(b_addr, kB2SlotBytes / 2)
-                                                 : umma_desc_kmajor_sw128(b_addr);
-                constexpr int b_step = kMN != 0 ? 128 : 2;
+                // MN-major Y boxes: 16 contraction rows (columns j) of 128 B = +2048 B per K = 16 step
+                const uint64_t b_desc = umma_desc_mnmajor_sw128(
+                    smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes), kB2SlotBytes / 2);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + b_step * k, idesc_acc,
+                  tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 128 * k, idesc_acc,
                                    (lt | p | js | k) != 0 ? 1u : 0u);
               }
               tc_commit_pair(&bars.empty[s]);
@@ -315,14 +304,6 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       }
       if (elect_one()) tc_commit_pair(&bars.acc_full);
       __syncwarp();
-      if (timed && lane == 0) {
-        my_t[3] = clock64() - t_start;
-        my_t[4] = w_x;
-        my_t[5] = w_te;
-        my_t[6] = w_fz;
-        my_t[7] = w_gf;
-        my_t[8] = w_fy;
-      }
     }
   } else if (warp < kB2EpiWarps) {
     // ------------------------------------------------------------ epilogue: z -> G (bf16, swizzled smem)
@@ -340,30 +321,37 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
     const float neg_lr = -rc.x;
     const int diag_col = diag0 + row0 + r_loc;
     const int warp_diag_lo = diag0 + row0 + (q & 1) * 32;
-    long long w_cf = 0, w_tf = 0, w_ge = 0;
-    auto epi_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
-      if constexpr ((kTune & 2) != 0) {
-        mbar_wait_hint(bar, parity, 4000u);
-        __syncwarp();
-      } else {
-        mbar_wait_warp(bar, parity, timed, acc);
-      }
-    };
     const uint32_t coef_u32 = smem_u32(smem_coef);
     const uint32_t g_u32 = smem_u32(smem_g);
+    const uint32_t g_off = static_cast<uint32_t>(js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128);
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
       const uint32_t par = (lt >> 1) & 1;
-      epi_wait(&bars.coef_full[buf], par, w_cf);
-      epi_wait(&bars.tmem_full[buf], par, w_tf);
+      mbar_wait_warp(&bars.coef_full[buf], par);
+      mbar_wait_warp(&bars.tmem_full[buf], par);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kB2ZCol + buf * 128 + hh * 32, r);
-      const float4* cf = reinterpret_cast<const float4*>(smem_coef + buf * kB2CoefBytes) + col_in_step;
+      const uint32_t cf = coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + col_in_step * 16);
       const int col0 = (t_begin + lt) * kB2TileN + col_in_step;
       const bool has_diag = (col0 + 32 > warp_diag_lo) && (col0 < warp_diag_lo + 32);  // warp-uniform
       const bool ragged = col0 + 32 > n_cols;                                           // warp-uniform
       tmem_ld_wait();
+      // dL/dz of one element (fp32): row term + column term, own-column soft target, ragged-edge mask
+      auto g_of = [&](int j) {
+        const float z = __uint_as_float(r[j]);
+#ifdef SCL_LAB_NO_EPI
+        return z;
+#else
+        const float4 cc = lds_v4(cf + static_cast<uint32_t>(j * 16));  // smem broadcast (same address across the warp)
+        const float p = ex2_approx(fmaf(z, s2, neg_lr));
+        const float pc = ex2_approx(fmaf(z, s2, -cc.x));
+        float g = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
+        if (has_diag) g -= (j == diag_col - col0) ? rc.w : 0.f;
+        if (ragged) g = (col0 + j < n_cols) ? g : 0.f;
+        return g;
+#endif
+      };
       if constexpr (kSplit != 0) {
         // fp32-accurate mode: G = G1 + G2 (two bf16 tiles).  z already sits in registers, so TMEM goes back first;
         // the arithmetic then runs 8 columns at a time straight into the two 16-byte stores (low register pressure;
@@ -374,36 +362,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           if (leader) mbar_arrive(&bars.tmem_empty[buf]);
           else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
         }
-        epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
-        const int g_off = js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
+        mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const int j = ch * 8 + jj * 2;
-            float g2[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float z = __uint_as_float(r[j + e]);
-              const float4 cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
-              const float p = ex2_approx(fmaf(z, s2, neg_lr));
-              const float pc = ex2_approx(fmaf(z, s2, -cc.x));
-              g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
-            }
-            if (has_diag) {
-              const int di = diag_col - col0;
-              g2[0] -= (j == di) ? rc.w : 0.f;
-              g2[1] -= (j + 1 == di) ? rc.w : 0.f;
-            }
-            if (ragged) {
-              g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
-              g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
-            }
-            hi[jj] = pack_bf16x2(g2[0], g2[1]);
-            lo[jj] = pack_bf16x2(g2[0] - __uint_as_float(hi[jj] << 16), g2[1] - __uint_as_float(hi[jj] & 0xffff0000u));
+            const float g0 = g_of(ch * 8 + jj * 2), g1 = g_of(ch * 8 + jj * 2 + 1);
+            hi[jj] = pack_bf16x2(g0, g1);
+            lo[jj] = pack_bf16x2(g0 - __uint_as_float(hi[jj] << 16), g1 - __uint_as_float(hi[jj] & 0xffff0000u));
           }
-          const uint32_t off = static_cast<uint32_t>(g_off + (((c16 + ch) ^ (r_loc & 7)) * 16));
+          const uint32_t off = g_off + static_cast<uint32_t>(((c16 + ch) ^ (r_loc & 7)) * 16);
           sts_v4(g_u32 + off, hi[0], hi[1], hi[2], hi[3]);
           sts_v4(g_u32 + kB2GBytes + off, lo[0], lo[1], lo[2], lo[3]);
         }
@@ -412,31 +381,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
       } else {
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float g2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float z = __uint_as_float(r[j + e]);
-            float4 cc;  // smem broadcast (same address across the warp)
-            if constexpr ((kTune & 1) != 0)
-              cc = lds_v4(coef_u32 + static_cast<uint32_t>(buf * kB2CoefBytes + (col_in_step + j + e) * 16));
-            else
-              cc = cf[j + e];
-            const float p = ex2_approx(fmaf(z, s2, neg_lr));
-            const float pc = ex2_approx(fmaf(z, s2, -cc.x));
-            g2[e] = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
-          }
-          if (has_diag) {
-            const int di = diag_col - col0;
-            g2[0] -= (j == di) ? rc.w : 0.f;
-            g2[1] -= (j + 1 == di) ? rc.w : 0.f;
-          }
-          if (ragged) {
-            g2[0] = (col0 + j < n_cols) ? g2[0] : 0.f;
-            g2[1] = (col0 + j + 1 < n_cols) ? g2[1] : 0.f;
-          }
-          packed[j >> 1] = pack_bf16x2(g2[0], g2[1]);
-        }
+        for (int j = 0; j < 32; j += 2) packed[j >> 1] = pack_bf16x2(g_of(j), g_of(j + 1));
         // z is in registers now: hand the TMEM buffer back before the (possibly waiting) G write
         tc_fence_before();
         __syncwarp();
@@ -446,18 +391,11 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
           else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
         }
         // single G buffer: the second GEMM of the previous step must have consumed it
-        epi_wait(&bars.g_empty, (lt & 1) ^ 1, w_ge);
-        uint8_t* g_row = smem_g + js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128;
+        mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = (c16 + ch) ^ (r_loc & 7);  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
-          if constexpr ((kTune & 1) != 0)
-            sts_v4(g_u32 + static_cast<uint32_t>(js * kB2GSubBytes + (r_loc >> 3) * 1024 + (r_loc & 7) * 128 + chunk * 16),
-                   packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-          else
-            *reinterpret_cast<uint4*>(g_row + chunk * 16) =
-                make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-        }
+        for (int ch = 0; ch < 4; ++ch)  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
+          sts_v4(g_u32 + g_off + static_cast<uint32_t>(((c16 + ch) ^ (r_loc & 7)) * 16), packed[ch * 4 + 0],
+                 packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -466,15 +404,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,    // X   [M, 
         else mbar_arrive_remote(&bars.g_full, 0);
       }
     }
-    if (timed && warp == 0 && lane == 0) {
-      my_t[9] = clock64() - t_start;
-      my_t[10] = w_cf;
-      my_t[11] = w_tf;
-      my_t[12] = w_ge;
-      my_t[13] = n_my;
-    }
     // ---- drain this CTA's 64-row slice of the dX accumulators (warp hh takes chunk hh of each group)
-    { long long unused = 0; mbar_wait_warp(&bars.acc_full, 0, false, unused); }
+    mbar_wait_warp(&bars.acc_full, 0);
     tc_fence_after();
     float* out_row = dx_partial + (static_cast<size_t>(blockIdx.y) * m_pad + row0 + r_loc) * d;
     for (int g = 0; g < ng; ++g) {
@@ -514,80 +445,45 @@ size_t bwd_pair_smem_bytes(int d, int split) {
   return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
 }
 
-// developer knob, read once per process: SCL_BWD_MN=1 -> no transposed copies, MN-major B operand in the gradient GEMM
-bool bwd_pair_mn_major() {
-  static const bool on = [] {
-    const char* e = std::getenv("SCL_BWD_MN");
-    return e != nullptr && e[0] == '1' && e[1] == 0;
-  }();
-  return on;
-}
-
+// Column chunks of the backward grid.  Every chunk adds one [m_rows, D] fp32 slab that the kernel writes and
+// bwd_gather reads back (~4 us at 4096 x 512 = 0.9 of a tile-step): charged per chunk, scaled by the slab size.
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 127) / 128 * max(1, bwd_pair_d_slices(d));
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
-  if (const int c = chunks_override("SCL_BWD_CHUNKS", n_tiles, tiles_per_chunk)) return c;
-  return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
+  const double slab_cost = 0.9 * (static_cast<double>(m_rows) / 4096.0) * (static_cast<double>(d) / 512.0);
+  return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, slab_cost, tiles_per_chunk);
 }
 
-template <int kTune, int kSplit, int kMN>
+template <int kSplit>
 static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols,
-                                          const CUtensorMap& tm_cols_t, int m_rows, int n_cols, int d, int chunks,
+                                          const CUtensorMap& tm_cols_mn, int m_rows, int n_cols, int d, int chunks,
                                           int tiles_per_chunk, int m_pad, int diag0, const float* scale_log2,
                                           const float4* row_coef, const float4* col_coef, float* dx_partial,
-                                          long long* dbg_t, cudaStream_t stream) {
+                                          cudaStream_t stream) {
   const size_t smem = bwd_pair_smem_bytes(d, kSplit);
-  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kTune, kSplit, kMN>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
-    if (err != cudaSuccess) return err;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state)
+  cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         231424);
+  if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 127) / 128;
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);
   dim3 grid(2 * pairs, chunks, d_slices);
-  bwd_rows_pair_kernel<kTune, kSplit, kMN><<<grid, kB2Threads, smem, stream>>>(
-      tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, d_slices, n_tiles, tiles_per_chunk, m_pad, diag0, scale_log2,
-      row_coef, col_coef, dx_partial, dbg_t);
+  bwd_rows_pair_kernel<kSplit><<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d,
+                                                                   d_slices, n_tiles, tiles_per_chunk, m_pad, diag0,
+                                                                   scale_log2, row_coef, col_coef, dx_partial);
   return cudaGetLastError();
 }
 
-cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_mn,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, long long* dbg_t, int split, cudaStream_t stream) {
+                                 float* dx_partial, int split, cudaStream_t stream) {
   if (split)
-    return launch_bwd_rows_pair_t<0, 1, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                           diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-  static const int tune = [] {  // developer knob, read once per process
-    const char* e = std::getenv("SCL_BWD_TUNE");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : 0;
-  }();
-  if (bwd_pair_mn_major())
-    return tune >= 3 ? launch_bwd_rows_pair_t<3, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
-                                                       tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
-                                                       dx_partial, dbg_t, stream)
-                     : launch_bwd_rows_pair_t<0, 0, 1>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks,
-                                                       tiles_per_chunk, m_pad, diag0, scale_log2, row_coef, col_coef,
-                                                       dx_partial, dbg_t, stream);
-  switch (tune) {
-    case 1: return launch_bwd_rows_pair_t<1, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 2: return launch_bwd_rows_pair_t<2, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 3: return launch_bwd_rows_pair_t<3, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                             diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    case 7: return launch_bwd_rows_pair_t<7, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
-                                                diag0, scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
-    default: break;  // (4, 5, 6 are not instantiated)
-  }
-  return launch_bwd_rows_pair_t<0, 0, 0>(tm_rows, tm_cols, tm_cols_t, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
-                                   scale_log2, row_coef, col_coef, dx_partial, dbg_t, stream);
+    return launch_bwd_rows_pair_t<1>(tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad,
+                                     diag0, scale_log2, row_coef, col_coef, dx_partial, stream);
+  return launch_bwd_rows_pair_t<0>(tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, diag0,
+                                   scale_log2, row_coef, col_coef, dx_partial, stream);
 }
 
 }  // namespace scl

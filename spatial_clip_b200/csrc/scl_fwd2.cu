@@ -1,19 +1,15 @@
-// Forward row-statistics kernel, CTA-pair version (tcgen05 cta_group::2, cluster of 2 CTAs).
+// Forward row-statistics kernel (tcgen05 cta_group::2, cluster of 2 CTAs).
 //
-// Same contract as fwd_rowstats_kernel (scl_fwd.cu) -- online row max / sum / first and second moments of
-// z = X . Y^T -- but one UMMA instruction spans two SMs: the pair owns 256 rows (128 per CTA), each CTA
-// loads only ITS half of every 256-column Y tile (16 KB per K-chunk instead of 32 KB), and the leader
-// CTA's single MMA thread issues 256x256x16 instructions that read both CTAs' shared memory.  Halving
-// the per-SM operand traffic frees shared memory for a 6-deep TMA ring (the 3-deep ring of the
-// single-CTA kernel left the tensor pipe waiting on TMA ~1/3 of the time, profiles/r1_*).
+// Online row max / sum / first and second moments of z = X . Y^T.  One UMMA instruction spans two SMs: the pair
+// owns 256 rows (128 per CTA), each CTA loads only ITS half of every 256-column Y tile (16 KB per K-chunk), and the
+// leader CTA's single MMA thread issues 256x256x16 instructions that read both CTAs' shared memory.  The X block
+// stays resident (128 KB at D = 512) next to a 6-deep TMA ring.
 //
 // Barrier protocol (all barriers live at the same smem offset in both CTAs):
 //   a_full, full[s]   waited on by the leader only; both CTAs' TMA loads credit the LEADER's barrier
 //   empty[s]          each CTA's producer waits on its own copy; the leader's tcgen05.commit multicasts
 //   tmem_full[b]      each CTA's epilogue waits on its own copy (multicast commit)
 //   tmem_empty[b]     leader only, 16 arrivals: the 8 epilogue warps of both CTAs (peer arrives remotely)
-#include <cstdlib>
-
 #include "scl_kernels.h"
 #include "scl_ptx.cuh"
 
@@ -54,13 +50,10 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
                          const __grid_constant__ CUtensorMap tm_cols,  // Y [N, D], box {64, 128}
                          int m_rows, int n_cols, int d, int n_tiles, int tiles_per_chunk, int m_pad,
                          const float* __restrict__ scale_log2_ptr, float4* __restrict__ partial,
-                         float* __restrict__ dbg_z, int dbg_ld, long long* __restrict__ dbg_t,
+                         float* __restrict__ dbg_z, int dbg_ld,
                          const float* __restrict__ diag_z, int loc_lo, int loc_hi, int* __restrict__ rank_part) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ F2Bars bars;
-  const bool timed = dbg_t != nullptr;  // developer timing mode: cycles spent in each wait, per CTA
-  long long* my_t = timed ? dbg_t + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
-  const long long t_start = timed ? clock64() : 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = d / kF2BK;
   // D <= 512: the X block stays resident (nk x 16 KB) and the ring carries only Y chunks (16 KB stages).
@@ -111,21 +104,16 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
           tma_load_2d_pair(smem_a + kc * kF2AChunkBytes, &tm_rows, &bars.a_full, kc * kF2BK, row0);
       }
       int it = 0;
-      long long w_empty = 0;
       for (int lt = 0; lt < n_my; ++lt) {
         const int col0 = (t_begin + lt) * kF2TileN + static_cast<int>(cta) * 128;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
-          mbar_wait_t(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1, timed, w_empty);
+          mbar_wait(&bars.empty[s], ((it / kF2Stages) & 1) ^ 1);
           if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * stage_bytes));
           tma_load_2d_pair(smem_b + s * stage_bytes, &tm_cols, &bars.full[s], kc * kF2BK, col0);
           if (stream_x)
             tma_load_2d_pair(smem_b + s * stage_bytes + kF2BStageBytes, &tm_rows, &bars.full[s], kc * kF2BK, row0);
         }
-      }
-      if (timed) {
-        my_t[0] = clock64() - t_start;  // producer lifetime
-        my_t[1] = w_empty;
       }
     }
   } else if (warp == kF2MmaWarp) {
@@ -134,18 +122,17 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     // tcgen05 instructions, so the compiler emits them straight-line instead of per-active-lane loops.
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, kF2TileN);
-      long long w_a = 0, w_te = 0, w_full = 0;
-      if (!stream_x) mbar_wait_warp(&bars.a_full, 0, timed, w_a);
+      if (!stream_x) mbar_wait_warp(&bars.a_full, 0);
       tc_fence_after();
       int it = 0;
       for (int lt = 0; lt < n_my; ++lt) {
         const int buf = lt & 1;
-        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1, timed, w_te);
+        mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kF2TileN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % kF2Stages;
-          mbar_wait_warp(&bars.full[s], (it / kF2Stages) & 1, timed, w_full);
+          mbar_wait_warp(&bars.full[s], (it / kF2Stages) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(
@@ -160,12 +147,6 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
           __syncwarp();
         }
       }
-      if (timed && lane == 0) {
-        my_t[2] = clock64() - t_start;  // MMA warp lifetime (issue side)
-        my_t[3] = w_a;
-        my_t[4] = w_te;
-        my_t[5] = w_full;
-      }
     }
   } else if (warp < kF2EpiWarps) {
     // ------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
@@ -176,13 +157,12 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
     const int row = row0 + q * 32 + lane;
     const float s2 = __ldg(scale_log2_ptr);
     float m = -INFINITY, s_e = 0.f, s_ez = 0.f, s_ezz = 0.f;
-    long long w_tf = 0;
     int above = 0;  // kRank: local columns scoring above this row's own pair
     float zd = 0.f;
     if constexpr (kRank != 0) zd = row < m_rows ? __ldg(diag_z + row) : INFINITY;
     for (int lt = 0; lt < n_my; ++lt) {
       const int buf = lt & 1;
-      mbar_wait_warp(&bars.tmem_full[buf], (lt >> 1) & 1, timed, w_tf);
+      mbar_wait_warp(&bars.tmem_full[buf], (lt >> 1) & 1);
       tc_fence_after();
       const int tile_col0 = (t_begin + lt) * kF2TileN + hh * 64;
 #pragma unroll 1
@@ -277,11 +257,6 @@ fwd_rowstats_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,  // X [M, 
         else mbar_arrive_remote(&bars.tmem_empty[buf], 0);
       }
     }
-    if (timed && warp == 0 && lane == 0) {
-      my_t[6] = clock64() - t_start;  // epilogue warp lifetime
-      my_t[7] = w_tf;
-      my_t[8] = n_my;
-    }
     const int slot = blockIdx.y * 4 + hh;
     partial[static_cast<size_t>(slot) * m_pad + row] = make_float4(m, s_e, s_ez, s_ezz);
     if constexpr (kRank != 0) rank_part[static_cast<size_t>(slot) * m_pad + row] = above;
@@ -303,43 +278,34 @@ size_t fwd_pair_smem_bytes(int d) {
 int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk) {
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
-  if (const int c = chunks_override("SCL_FWD_CHUNKS", n_tiles, tiles_per_chunk)) return c;
-  return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, tiles_per_chunk);
+  return pick_chunks_balanced(pairs, n_tiles, num_sms / 2, 2, 0.02, tiles_per_chunk);
 }
 
 template <int kRank>
 static cudaError_t launch_fwd_rowstats_pair_t(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
                                               int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
                                               const float* scale_log2, float4* partial, float* dbg_z, int dbg_ld,
-                                              long long* dbg_t, const float* diag_z, int loc_lo, int loc_hi,
-                                              int* rank_part, cudaStream_t stream) {
+                                              const float* diag_z, int loc_lo, int loc_hi, int* rank_part,
+                                              cudaStream_t stream) {
   const size_t smem = fwd_pair_smem_bytes(d);
-  // opt in to > 48 KB dynamic shared memory once per device (the attribute is sticky; 227 KB covers every D)
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t err =
-        cudaFuncSetAttribute(fwd_rowstats_pair_kernel<kRank>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
-    if (err != cudaSuccess) return err;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state)
+  cudaError_t err =
+      cudaFuncSetAttribute(fwd_rowstats_pair_kernel<kRank>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+  if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;
   dim3 grid(2 * pairs, chunks);
   fwd_rowstats_pair_kernel<kRank><<<grid, kF2Threads, smem, stream>>>(tm_rows, tm_cols, m_rows, n_cols, d, n_tiles,
                                                                       tiles_per_chunk, m_pad, scale_log2, partial,
-                                                                      dbg_z, dbg_ld, dbg_t, diag_z, loc_lo, loc_hi,
-                                                                      rank_part);
+                                                                      dbg_z, dbg_ld, diag_z, loc_lo, loc_hi, rank_part);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
                                      int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
-                                     float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
-                                     cudaStream_t stream) {
+                                     float4* partial, float* dbg_z, int dbg_ld, cudaStream_t stream) {
   return launch_fwd_rowstats_pair_t<0>(tm_rows, tm_cols, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, scale_log2,
-                                       partial, dbg_z, dbg_ld, dbg_t, nullptr, 0, 0, nullptr, stream);
+                                       partial, dbg_z, dbg_ld, nullptr, 0, 0, nullptr, stream);
 }
 
 cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
@@ -347,7 +313,7 @@ cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUt
                                            const float* scale_log2, float4* partial, const float* diag_z, int loc_lo,
                                            int loc_hi, int* rank_part, cudaStream_t stream) {
   return launch_fwd_rowstats_pair_t<1>(tm_rows, tm_cols, m_rows, n_cols, d, chunks, tiles_per_chunk, m_pad, scale_log2,
-                                       partial, nullptr, 0, nullptr, diag_z, loc_lo, loc_hi, rank_part, stream);
+                                       partial, nullptr, 0, diag_z, loc_lo, loc_hi, rank_part, stream);
 }
 
 }  // namespace scl

@@ -2,32 +2,18 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
-#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace scl {
 
-// ---- tensor-core kernels
-size_t fwd_smem_bytes(int d);
-int fwd_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
-cudaError_t launch_fwd_rowstats(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols, int d,
-                                int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2, float4* partial,
-                                float* dbg_z, int dbg_ld, cudaStream_t stream);
-
-size_t bwd_smem_bytes();
-void bwd_pick_split(int d, int* n_dsplit, int* dn);
-int bwd_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
-cudaError_t launch_bwd_rows(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
-                            int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
-                            const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                            float* dx_partial, cudaStream_t stream);
-
-// ---- CTA-pair (cta_group::2) variants
-// Column chunking for a grid of `units` row blocks (CTAs or CTA pairs) over `slots` concurrently resident
-// units: choose the chunk count that minimises  waves * tiles_per_chunk  (the launch lasts `waves` rounds of
-// the longest chunk), breaking ties towards fewer chunks (each chunk adds a partial-result slab).
-inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles, int* tiles_per_chunk) {
+// ---- tensor-core kernels (CTA pairs, tcgen05 cta_group::2)
+// Column chunking for a grid of `units` row blocks (CTA pairs) over `slots` concurrently resident units: choose the
+// chunk count that minimises  waves * (tiles_per_chunk + per-CTA overhead) + chunks * chunk_cost  -- the launch
+// lasts `waves` rounds of the longest chunk, and every chunk adds a partial-result slab over all rows that a later
+// pass reads back (`chunk_cost`, in tile-steps) -- breaking ties towards fewer chunks.
+inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles, double chunk_cost,
+                                int* tiles_per_chunk) {
   int best_c = 1, best_tpc = n_tiles;
   double best_cost = 1e30;
   const int max_c = n_tiles / min_tiles > 1 ? n_tiles / min_tiles : 1;
@@ -36,7 +22,7 @@ inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles
     const int real_c = (n_tiles + tpc - 1) / tpc;
     const long long ctas = static_cast<long long>(units) * real_c;
     const long long waves = (ctas + slots - 1) / slots;
-    const double cost = static_cast<double>(waves) * (tpc + 0.35) + 0.02 * real_c;
+    const double cost = static_cast<double>(waves) * (tpc + 0.35) + chunk_cost * real_c;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best_c = real_c;
@@ -46,24 +32,11 @@ inline int pick_chunks_balanced(int units, int n_tiles, int slots, int min_tiles
   *tiles_per_chunk = best_tpc;
   return best_c;
 }
-// Developer knob: SCL_FWD_CHUNKS / SCL_BWD_CHUNKS = c > 0 overrides the picker of the CTA-pair kernels with (about) c
-// column chunks (plans and work-area sizes follow, they all go through the pickers).  Unset: the balanced choice.
-inline int chunks_override(const char* env_name, int n_tiles, int* tiles_per_chunk) {
-  const char* e = std::getenv(env_name);
-  if (e == nullptr || e[0] == 0) return 0;
-  const int c = std::atoi(e);
-  if (c <= 0) return 0;
-  const int cc = c < n_tiles ? c : n_tiles;
-  const int tpc = (n_tiles + cc - 1) / cc;
-  *tiles_per_chunk = tpc;
-  return (n_tiles + tpc - 1) / tpc;
-}
 size_t fwd_pair_smem_bytes(int d);
 int fwd_pair_pick_chunks(int m_rows, int n_cols, int num_sms, int* tiles_per_chunk);
 cudaError_t launch_fwd_rowstats_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows, int n_cols,
                                      int d, int chunks, int tiles_per_chunk, int m_pad, const float* scale_log2,
-                                     float4* partial, float* dbg_z, int dbg_ld, long long* dbg_t,
-                                     cudaStream_t stream);
+                                     float4* partial, float* dbg_z, int dbg_ld, cudaStream_t stream);
 cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, int m_rows,
                                            int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad,
                                            const float* scale_log2, float4* partial, const float* diag_z, int loc_lo,
@@ -71,15 +44,14 @@ cudaError_t launch_fwd_rowstats_pair_ranks(const CUtensorMap& tm_rows, const CUt
 size_t bwd_pair_smem_bytes(int d, int split);
 int bwd_pair_pick_chunks(int m_rows, int n_cols, int d, int num_sms, int* tiles_per_chunk);
 int bwd_pair_d_slices(int d);
-bool bwd_pair_mn_major();
-cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_t,
+cudaError_t launch_bwd_rows_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_cols, const CUtensorMap& tm_cols_mn,
                                  int m_rows, int n_cols, int d, int chunks, int tiles_per_chunk, int m_pad, int diag0,
                                  const float* scale_log2, const float4* row_coef, const float4* col_coef,
-                                 float* dx_partial, long long* dbg_t, int split, cudaStream_t stream);
+                                 float* dx_partial, int split, cudaStream_t stream);
 
 // ---- HBM-bound side passes (scl_aux.cu)
-cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, void* y_t, int rows, int d, int ld_t,
-                             int normalize, cudaStream_t stream);
+cudaError_t launch_cast_bf16(const void* x, int src_dtype, void* y, int rows, int d, int normalize,
+                             cudaStream_t stream);
 cudaError_t launch_prep_scalars(const float* logit_scale, float cap, float* scalars, cudaStream_t stream);
 cudaError_t launch_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids,
                                    const float* nbr_alpha, int b_local, int k, float alpha_scale, int rank,
@@ -90,7 +62,9 @@ cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, i
                                 const void* y_all, const int32_t* pos_col, const float* pos_q, int kp1,
                                 float4* row_stats, cudaStream_t stream);
 cudaError_t launch_reduce_rows(const float4* stats_a, const float4* stats_b, int m_rows, const float* scalars,
-                               float* sums6, cudaStream_t stream);
+                               float* sums6, float c, float w, float* out4, cudaStream_t stream);
+cudaError_t launch_prepare(const void* image, const void* text, int src_dtype, int rows, int d, void* image_bf16,
+                           void* text_bf16, const float* logit_scale, float cap, float* scalars, cudaStream_t stream);
 cudaError_t launch_loss_scalars(const float* sums6, const float* scalars, float c, float w, float* out4,
                                 cudaStream_t stream);
 cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, const float4* col_stats, int n_cols,
@@ -102,12 +76,15 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
                               const int32_t* pos_col, const float* pos_q, int kp1, const int32_t* opp_col_all,
                               const float* opp_q_all, int n_global, int b_local, int rank, const float* gaps,
                               const float* scalars, const float* grad_out, float c, float w, float mult, int col_mode,
-                              int split, float* dx32, void* dx_out, int out_dtype, cudaStream_t stream);
+                              int split, void* workspace, size_t workspace_bytes, void* dx_out, int out_dtype,
+                              cudaStream_t stream);
+size_t bwd_finish_workspace_bytes(int n_global, int b_local, int kp1);
+cudaError_t launch_check_positives(const int32_t* col_in, const float* q_in, int b_local, int kp1, int n_global,
+                                   int rank, int32_t* col_out, float* q_out, int* flag, cudaStream_t stream);
 
 // ---- fp32-accurate ("bf16x2") operand preparation (scl_split.cu)
 cudaError_t launch_split_cast(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d,
                               cudaStream_t stream);
-cudaError_t launch_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, cudaStream_t stream);
 
 // ---- in-pass retrieval ranks (scl_rank.cu)
 cudaError_t launch_retrieval_diag(const void* x_rows, int m_rows, const void* y_cols, int d, int first_col,

@@ -60,50 +60,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// try_wait with a suspend-time hint (ns): the thread may stay parked that long before the instruction returns
-// false, so a long wait costs a handful of barrier reads instead of one every ~100 cycles (each try_wait is a
-// shared-memory access; the backward kernel is shared-memory-port bound, profiles/r1_smem_port_accounting.md)
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t spins = 0;
-  // every unsuccessful try may have parked for up to hint_ns: keep the watchdog in seconds, not minutes
-  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
-    if (++spins > (SCL_SPIN_LIMIT >> 7)) __trap();
-  }
-}
-
 // Warp-level wait: every lane polls (the hardware parks a fully waiting warp), then the warp re-converges.
 // Measured: letting ONE lane poll while 31 sit at the warp barrier is ~2.6x slower for the whole kernel.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if (timed) {
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-  } else {
-    mbar_wait(bar, parity);
-  }
-  __syncwarp();
-}
-
-// wait that adds the cycles spent to *acc when `timed` (developer timing mode of the tensor-core kernels)
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if (!timed) {
-    mbar_wait(bar, parity);
-    return;
-  }
-  const long long t0 = clock64();
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   mbar_wait(bar, parity);
-  acc += clock64() - t0;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- TMA

@@ -2,7 +2,7 @@
 // h = bf16(x), l = bf16(x - h) (|x - h - l| <= 2^-18 |x|), laid out so that the UNCHANGED bf16 tensor-core
 // kernels compute x.y ~= xh.yh + xh.yl + xl.yh by contracting over K-concatenated rows of width 3 d:
 //   row operand     X' = (h | h | l)        column operand  Y' = (h | l | h)
-// and, for the gradient GEMM, the stacked transposed copy [Yh^T ; Yl^T] ([2 d, ld]).  HBM-bound, coalesced.
+// (the gradient GEMM reads Yh / Yl as the column ranges [0, d) / [d, 2 d) of Y', MN-major).  HBM-bound, coalesced.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -73,43 +73,6 @@ __global__ void __launch_bounds__(256) split_cast_kernel(const T* __restrict__ x
   }
 }
 
-// dst[c][r] = src[r][c] for the first n_cols columns of a row-major bf16 matrix with row pitch src_ld;
-// one CTA per 64 x 64 tile, 16-byte loads and (full tiles) 16-byte transposed stores through a skewed smem tile
-__global__ void __launch_bounds__(256) transpose_cols_kernel(const __nv_bfloat16* __restrict__ src, int src_ld,
-                                                             int n_rows, int n_cols, __nv_bfloat16* __restrict__ dst,
-                                                             int ld_t) {
-  __shared__ __align__(16) __nv_bfloat16 tile[64][120];  // [row][col + 8 * (row / 8)], see cast_bf16_kernel
-  const int r0 = blockIdx.x * 64;
-  const int c0 = blockIdx.y * 64;
-  const int lr = threadIdx.x >> 3;       // 0..31
-  const int c8 = (threadIdx.x & 7) * 8;  // 8 consecutive columns
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int rr = lr + 32 * pass;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r0 + rr < n_rows) v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r0 + rr) * src_ld + c0 + c8);
-    *reinterpret_cast<uint4*>(&tile[rr][c8 + 8 * (rr >> 3)]) = v;
-  }
-  __syncthreads();
-  const int sr = (threadIdx.x & 7) * 8;  // 8 consecutive source rows
-  const bool full = r0 + 64 <= n_rows && (ld_t % 8) == 0;
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int cc = (threadIdx.x >> 3) + 32 * pass;
-    __align__(16) __nv_bfloat16 col[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) col[k] = tile[sr + k][cc + sr];
-    __nv_bfloat16* out = dst + static_cast<size_t>(c0 + cc) * ld_t + r0 + sr;
-    if (full) {
-      *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(col);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (r0 + sr + k < n_rows) out[k] = col[k];
-    }
-  }
-}
-
 }  // namespace
 
 cudaError_t launch_split_cast(const void* x, int src_dtype, void* rows_out, void* cols_out, int rows, int d,
@@ -125,15 +88,6 @@ cudaError_t launch_split_cast(const void* x, int src_dtype, void* rows_out, void
     split_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ro, co, rows, d);
   else
     split_cast_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), ro, co, rows, d);
-  return cudaGetLastError();
-}
-
-// cols_all: gathered column operand [n_rows, 3 d] = (h | l | h); out_t: [2 d, ld_t] = [h^T ; l^T]
-cudaError_t launch_transpose_split(const void* cols_all, int n_rows, int d, int ld_t, void* out_t, cudaStream_t stream) {
-  if (n_rows <= 0) return cudaSuccess;
-  dim3 grid((n_rows + 63) / 64, 2 * d / 64);
-  transpose_cols_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(cols_all), 3 * d, n_rows, 2 * d,
-                                                  static_cast<__nv_bfloat16*>(out_t), ld_t);
   return cudaGetLastError();
 }
 

@@ -65,32 +65,24 @@ def _set_ops_for_testing(ops):
 # ------------------------------------------------------------------------------------------------
 # distributed plumbing (torch.distributed: NCCL on the GPU box, gloo in the CPU tests)
 # ------------------------------------------------------------------------------------------------
-def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
-    """Rank-major concatenation along dim 0 (== torch.cat(all_gather(...)), loss.py:51-57).
-
-    Moved as raw bytes so that bf16 / int32-bit-pattern payloads work on every backend (gloo has no
-    16-bit integer or bf16 all-gather)."""
-    t = t.contiguous()
-    carrier = t.view(torch.uint8).reshape(-1)
-    out = torch.empty(world * carrier.numel(), dtype=torch.uint8, device=t.device)
-    try:
-        dist.all_gather_into_tensor(out, carrier, group=group)
-    except (RuntimeError, NotImplementedError):
-        parts = [torch.empty_like(carrier) for _ in range(world)]
-        dist.all_gather(parts, carrier, group=group)
-        out = torch.cat(parts, dim=0)
-    return out.view(t.dtype).reshape((world * t.shape[0],) + tuple(t.shape[1:]))
-
-
 def _all_gather_rows_async(t: torch.Tensor, world: int, group):
-    """Non-blocking form of ``_all_gather_rows``: returns (gathered tensor, wait).  ``wait()`` makes the current
-    stream (NCCL) / the caller (gloo) wait for THIS exchange only, so later exchanges keep running underneath the
-    kernels that need only this one."""
+    """Rank-major concatenation along dim 0 (== torch.cat(all_gather(...)), loss.py:51-57), issued without waiting:
+    returns (gathered tensor, wait).  ``wait()`` makes the current stream (NCCL) / the caller (gloo) wait for THIS
+    exchange only, so later exchanges keep running underneath the kernels that need only this one.
+
+    Moved as raw bytes so that bf16 / int32-bit-pattern payloads work on every backend (gloo has no 16-bit integer or
+    bf16 all-gather)."""
     t = t.contiguous()
     carrier = t.view(torch.uint8).reshape(-1)
     out = torch.empty(world * carrier.numel(), dtype=torch.uint8, device=t.device)
     work = dist.all_gather_into_tensor(out, carrier, group=group, async_op=True)
     return out.view(t.dtype).reshape((world * t.shape[0],) + tuple(t.shape[1:])), work.wait
+
+
+def _all_gather_rows(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    out, wait = _all_gather_rows_async(t, world, group)
+    wait()
+    return out
 
 
 @dataclass
@@ -121,6 +113,9 @@ def _col_mode(cfg: _Cfg) -> int:
     return 0 if cfg.local_loss else 1
 
 
+_NEUTRAL_LSE = 1.0e30  # column statistics of rows that carry no gradient: exp2(z s - 1e30) == 0
+
+
 class _ContrastiveLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, image_tile_ids, text_tile_ids, neighbor_tile_ids,
@@ -135,34 +130,20 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if hasattr(ops, "check_shapes"):
             ops.check_shapes(b_local, n, d, cfg.split, any(ctx.needs_input_grad[:2]))
 
-        # ---- cap, bf16 copies (gather_features operands, loss.py:21-65).  Single rank + backward wanted: the
-        # transposed copies the backward GEMMs need come out of the same pass (dImage needs text^T and vice versa)
-        ld_t = (n + 7) // 8 * 8
-        # (grad mode is off inside Function.forward; needs_input_grad carries the intent)
-        no_t = getattr(ops, "mn_major", False) and not cfg.split  # developer knob: no transposed copies at all
-        fuse_t = world == 1 and not no_t
+        # ---- cap + bf16 copies of the local rows (the operands of gather_features, loss.py:21-65): one launch.
         # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
         # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
-        img_l, txt_l, img_c, txt_c, img_t, txt_t, scalars = ops.prepare(
-            image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap,
-            fuse_t and ctx.needs_input_grad[1], fuse_t and ctx.needs_input_grad[0], ld_t, split=cfg.split)
-        # Developer knob (SCL_OVERLAP_GATHER=1, W > 1): the exchanges are issued back to back without waiting -- gene
-        # features, tile ids, image features -- and the forward runs in three phases, each waiting only for the
-        # operand it reads, so the image-feature exchange runs underneath the image-rows pass (which needs only the
-        # gathered gene features).  Same collectives in the same order on every rank; off until run on a B200.
-        overlap = world > 1 and getattr(ops, "overlap_gather", False)
-        waits = None
-        if overlap:
-            txt_all, wait_txt = _all_gather_rows_async(txt_c, world, cfg.group)
-        elif world > 1:
-            img_all = _all_gather_rows(img_c, world, cfg.group)
-            txt_all = _all_gather_rows(txt_c, world, cfg.group)
-        else:
-            img_all, txt_all = img_c, txt_c
+        img_l, txt_l, img_c, txt_c, scalars = ops.prepare(
+            image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap, split=cfg.split)
 
-        # ---- tile ids (losses.py:63-68); plain CLIP has only the diagonal
+        # ---- exchanges (W > 1), all issued up front without waiting, in the order their consumers run: tile ids (one
+        # packed [2, B_l] record: both id vectors, losses.py:63-68) -> soft targets; gene features -> image-rows pass;
+        # image features -> text-rows pass.  Every phase waits only for the operand it reads, so the later exchanges
+        # run underneath the earlier phases' kernels.  The sequence of collectives depends on the configuration only.
         ids = None
         k = 0
+        waits = None
+        wait_ids = None
         if positives is not None:
             # soft targets resolved on the data side (positives.py): (columns int32, weights, probs) [B_l, K+1] of the
             # image rows, optionally followed by the same three for the text rows.  No id exchange, no hash build.
@@ -173,26 +154,31 @@ class _ContrastiveLossFn(torch.autograd.Function):
                         and image_tile_ids.shape == text_tile_ids.shape)
             img_ids = image_tile_ids.to(torch.int64).contiguous()
             txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
-            if overlap:
-                img_ids_all, wait_ids = _all_gather_rows_async(img_ids, world, cfg.group)
-                if same_ids:
-                    txt_ids_all = img_ids_all
-                else:
-                    txt_ids_all, wait_ids2 = _all_gather_rows_async(txt_ids, world, cfg.group)
-                    wait_ids = (lambda a=wait_ids, b=wait_ids2: (a(), b()))
-            elif world > 1:
-                img_ids_all = _all_gather_rows(img_ids, world, cfg.group)
-                txt_ids_all = img_ids_all if same_ids else _all_gather_rows(txt_ids, world, cfg.group)
+            if world > 1:
+                both, wait_ids = _all_gather_rows_async(torch.stack([img_ids, txt_ids]).reshape(1, 2, b_local), world,
+                                                        cfg.group)
+                ids_all = (both, None)  # [W, 2, B_l]; de-interleaved after the wait
             else:
-                img_ids_all, txt_ids_all = img_ids, txt_ids
-            ids = (img_ids_all, txt_ids_all, neighbor_tile_ids.to(torch.int64).contiguous(),
-                   neighbor_alphas.to(torch.float32).contiguous(), same_ids)
-        if overlap:
+                ids_all = (img_ids, txt_ids)
+            ids = [ids_all[0], ids_all[1], neighbor_tile_ids.to(torch.int64).contiguous(),
+                   neighbor_alphas.to(torch.float32).contiguous(), same_ids]
+        if world > 1:
+            txt_all, wait_txt = _all_gather_rows_async(txt_c, world, cfg.group)
             img_all, wait_img = _all_gather_rows_async(img_c, world, cfg.group)
-            waits = (wait_ids if ids is not None else None, wait_txt, wait_img)
+            if wait_ids is not None:
+                def wait_ids_and_split(w=wait_ids, rec=ids):
+                    w()
+                    rec[0], rec[1] = rec[0][:, 0].reshape(-1), rec[0][:, 1].reshape(-1)  # rank-major [N] each
+                    if rec[4]:
+                        rec[1] = rec[0]
+                waits = (wait_ids_and_split, wait_txt, wait_img)
+            else:
+                waits = (None, wait_txt, wait_img)
+        else:
+            img_all, txt_all = img_c, txt_c
 
         # ---- soft targets (losses.py:91-111), both fused similarity + online-LSE passes (losses.py:78-89,
-        # 113-121), row reductions and the loss scalars: one host call
+        # 113-121), row reductions and the loss scalars: one host call (one per phase when exchanges are in flight)
         global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
         c = 0.5 / (n if global_clip else b_local)
         (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
@@ -207,13 +193,11 @@ class _ContrastiveLossFn(torch.autograd.Function):
             out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
 
         ctx.cfg = cfg
-        ctx.no_t = no_t
         ctx.d = d
         ctx.c = c
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
         ctx.scale_shape = logit_scale.shape
         ctx.scale_device = logit_scale.device
-        ctx.transposed = (img_t, txt_t)  # None unless produced above
         ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
                               q_ti)
         if positives is not None:  # the caller already holds them: do not hand inputs back as outputs
@@ -230,68 +214,44 @@ class _ContrastiveLossFn(torch.autograd.Function):
         b_local, d = img_l.shape[0], ctx.d
         n = world * b_local
         go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        mode = _col_mode(cfg)
+        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
 
-        # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients
-        if world > 1:
+        # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients.  Only when other ranks'
+        # rows reach the local features at all: with a non-differentiable gather and local_loss (mode 0) the
+        # reference's backward has no collective either, and none is issued here.
+        if world > 1 and mode != 0:
             gap_rows = out4[1:2].reshape(1, 1)
             (stats_i_all, stats_t_all, col_it_all, q_it_all, col_ti_all, q_ti_all, gaps) = ops.exchange_records(
                 [stats_i, stats_t, col_it, q_it, col_ti, q_ti, gap_rows], world,
                 lambda t: _all_gather_rows(t, world, cfg.group))
             gaps = gaps.reshape(world)
+        elif world > 1:
+            # column statistics that switch the column-direction terms off (bwd_coeffs multiplies them by zero; the
+            # neutral LSE keeps the exponentials finite), this rank's gap in its slot, no opposite-direction lists
+            neutral = torch.zeros((n, 4), dtype=torch.float32, device=img_l.device)
+            neutral[:, 0] = _NEUTRAL_LSE
+            stats_i_all = stats_t_all = neutral
+            col_it_all = q_it_all = col_ti_all = q_ti_all = None
+            gaps = torch.zeros((world,), dtype=torch.float32, device=img_l.device)
+            gaps[rank:rank + 1] = out4[1:2]
         else:
             stats_i_all, stats_t_all = stats_i, stats_t
             col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti
             gaps = out4[1:2].contiguous()
 
-        mode = _col_mode(cfg)
-        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
         mult = float(world) if (global_clip and cfg.gather_with_grad) else 1.0
         w = cfg.temp_reg_weight
-        ld_t = (n + 7) // 8 * 8
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_scale = None
-        img_all_t, txt_all_t = ctx.transposed
-
-        def grad_image():
-            t = txt_all_t
-            if t is None and not ctx.no_t:
-                t = ops.transpose_split(txt_all, d, ld_t) if cfg.split else \
-                    ops.cast_bf16(txt_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
-            return ops.backward_dir(img_l, txt_all, t, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
-                                    b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0], q_ti,
-                                    split=cfg.split)
-
-        def grad_text():
-            t = img_all_t
-            if t is None and not ctx.no_t:
-                t = ops.transpose_split(img_all, d, ld_t) if cfg.split else \
-                    ops.cast_bf16(img_all, want_rows=False, want_t=True, ld_t=ld_t)[1]
-            return ops.backward_dir(txt_l, img_all, t, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
-                                    b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1], q_it,
-                                    split=cfg.split)
-
-        side = ops.side_stream(img_l.device) if (need_i and need_t and getattr(ops, "two_streams", False)) else None
-        if side is not None:
-            # Developer knob (SCL_BWD_STREAMS=1): the two directions are independent, so the gene-side chain
-            # (transposed copy, coefficients, tensor-core pass, finish) runs on a second stream and its short
-            # kernels fill the wave tails of the image-side pass.  Both streams start behind everything issued so
-            # far and the caller's stream continues behind both.
-            cur = torch.cuda.current_stream(img_l.device)
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                d_txt = grad_text()
-                join = torch.cuda.Event()
-                join.record(side)
-            d_img = grad_image()
-            cur.wait_event(join)
-            d_txt.record_stream(cur)
-        else:
-            if need_i:
-                d_img = grad_image()
-            if need_t:
-                d_txt = grad_text()
+        if need_i:
+            d_img = ops.backward_dir(img_l, txt_all, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
+                                     b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0], q_ti,
+                                     split=cfg.split)
+        if need_t:
+            d_txt = ops.backward_dir(txt_l, img_all, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
+                                     b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1], q_it,
+                                     split=cfg.split)
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(device=ctx.scale_device, dtype=ctx.in_dtypes[2]).reshape(ctx.scale_shape)
@@ -400,6 +360,54 @@ class SpatialLoss(_LossBase):
         return {"contrastive_loss": loss}
 
 
+class _ListCheck:
+    """Outcome of scl_check_positives for caller-resolved soft-target lists: a device flag that is read without
+    stalling the step.  The first ``sync_calls`` forwards block on it (a mis-configured producer -- e.g. local columns
+    on every rank -- fails on the first batch); afterwards the flag of step i is copied to pinned memory and examined at
+    step i + 1, so a bad batch still raises, one step late, at no synchronisation cost."""
+
+    BITS = ((1, "a column outside [-1, N) (such entries were dropped)"),
+            (2, "slot 0 of a row is not the row's own column rank * B_l + i (lists built for another rank / batch?)"),
+            (4, "an unused slot (column -1) carried weight"))
+
+    def __init__(self, sync_calls: int = 1):
+        self.sync_calls = sync_calls
+        self.calls = 0
+        self.pending = None  # (pinned host int32[1], event)
+
+    @classmethod
+    def _raise(cls, bits: int):
+        what = "; ".join(msg for bit, msg in cls.BITS if bits & bit)
+        raise ValueError(f"SpatialLossFromColumns: invalid positive_columns / positive_probs: {what}")
+
+    def submit(self, flags):
+        self.poll(block=False)
+        self.calls += 1
+        flag = flags[0] if len(flags) == 1 else flags[0] | flags[1]
+        if not flag.is_cuda or self.calls <= self.sync_calls:
+            bits = int(flag.reshape(-1)[0])
+            if bits:
+                self._raise(bits)
+            return
+        host = torch.empty((1,), dtype=torch.int32).pin_memory()
+        host.copy_(flag.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flag.device))
+        self.pending = (host, ev)
+
+    def poll(self, block: bool):
+        if self.pending is None:
+            return
+        host, ev = self.pending
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self.pending = None
+        if int(host[0]):
+            self._raise(int(host[0]))
+
+
 class SpatialLossFromColumns(SpatialLoss):
     """``SpatialLoss`` fed with soft targets that the data pipeline already resolved to global columns
     (producer: ``spatial_clip_b200.positives.resolve_positive_columns`` at collate time).
@@ -410,7 +418,16 @@ class SpatialLossFromColumns(SpatialLoss):
     (losses.py:91-111) leave the step altogether.  ``neighbor_alpha_scale`` is applied by the producer, not here.
     ``positive_*_text`` are the text-row lists when the two id vectors differ (the reference's loader makes them
     equal).  The LightningModule dispatches by parameter name (spatial_clip_module.py:44,58-61), so a collate that
-    adds these keys (``positives.collate_positive_columns``) is all the integration needs."""
+    adds these keys (``positives.collate_positive_columns``) is all the integration needs.
+
+    The lists come from outside the library, so every call passes them through ``scl_check_positives``: columns
+    outside [-1, N) are dropped before any kernel indexes with them, and a violated contract (range, slot 0 = own
+    column ``rank * B_l + i``, weight on an unused slot) raises ``ValueError`` -- synchronously on the first call, one
+    step late afterwards (``_ListCheck``)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._list_check = _ListCheck()
 
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
                 positive_columns: torch.Tensor, positive_probs: torch.Tensor,
@@ -423,13 +440,20 @@ class SpatialLossFromColumns(SpatialLoss):
         if positive_columns.dim() != 2 or positive_columns.shape[0] != b or \
                 positive_probs.shape != positive_columns.shape:
             raise ValueError("positive_columns / positive_probs must both be [B, K+1]")
+        if positive_columns.shape[1] > 32:
+            raise ValueError("at most 31 neighbour slots per row")
         if (positive_columns_text is None) != (positive_probs_text is None):
             raise ValueError("positive_columns_text and positive_probs_text go together")
         dev = image_features.device
+        rank, world = self.rank, self.world_size
+        ops = _ops()
+        flags = []
 
         def prep(col, q, w):
             col = col.to(device=dev, dtype=torch.int32).contiguous()
             q = q.to(device=dev, dtype=torch.float32).contiguous()
+            col, q, flag = ops.check_positives(col, q, world * b, rank)
+            flags.append(flag)
             w = q if w is None else w.to(device=dev, dtype=torch.float32).contiguous()
             return col, w, q
 
@@ -439,7 +463,8 @@ class SpatialLossFromColumns(SpatialLoss):
                     positive_probs_text.shape != positive_columns.shape:
                 raise ValueError("text-row lists must have the shape of the image-row lists")
             pos = pos + prep(positive_columns_text, positive_probs_text, None)
-        cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
+        self._list_check.submit(flags)
+        cfg = _Cfg("spatial", rank, world, self.local_loss, self.gather_with_grad,
                    self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
                    self.precision == "fp32", self.track_retrieval_ranks)
         loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,

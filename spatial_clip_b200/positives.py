@@ -15,10 +15,11 @@ id wins" map, same slot order, same fp32 accumulation order, same ``F.normalize(
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 __all__ = ["resolve_positive_columns", "collate_positive_columns"]
 
@@ -89,15 +90,22 @@ def resolve_positive_columns(all_tile_ids, neighbor_tile_ids, neighbor_alphas, n
     return torch.from_numpy(col), torch.from_numpy(w), torch.from_numpy(q)
 
 
-def collate_positive_columns(batch: dict, neighbor_alpha_scale: float = 1.0, all_tile_ids=None, rank: int = 0) -> dict:
+def collate_positive_columns(batch: dict, neighbor_alpha_scale: float = 1.0, all_tile_ids=None,
+                             rank: Optional[int] = None) -> dict:
     """Add ``positive_columns`` / ``positive_weights`` / ``positive_probs`` to a collated batch dictionary
     (the dictionary ``SpatialDataModule._collate_fn`` returns, spatial_datamodule.py:111-137).
 
-    Single process: the local batch IS the global batch, so the ids come from the batch itself.  Several ranks: pass
-    ``all_tile_ids`` (the sampler knows the global batch order) and ``rank``."""
+    Single process: the local batch IS the global batch, so the ids come from the batch itself.  Several ranks: the
+    columns are positions in the GLOBAL batch, so ``all_tile_ids`` (the sampler knows the global batch order) and
+    ``rank`` are required -- when torch.distributed is initialised with more than one rank, leaving them out raises
+    instead of silently producing rank 0's columns on every rank."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if multi and (all_tile_ids is None or rank is None):
+        raise ValueError("collate_positive_columns: torch.distributed is initialised with world_size > 1 -- pass "
+                         "all_tile_ids (tile ids of the global batch, rank-major) and rank")
     ids = batch["text_tile_ids"] if all_tile_ids is None else all_tile_ids
     col, w, q = resolve_positive_columns(ids, batch["neighbor_tile_ids"], batch["neighbor_alphas"],
-                                         neighbor_alpha_scale, rank)
+                                         neighbor_alpha_scale, 0 if rank is None else rank)
     out = dict(batch)
     out.update(positive_columns=col, positive_weights=w, positive_probs=q)
     return out

@@ -47,10 +47,3 @@ def text_ids_for(meta, batch):
 
         return shuffled_text_ids(batch.tile_ids, meta["text_ids_seed"])
     return batch.tile_ids.clone()
-
-
-def unverified_on_gpu(name):
-    """Fixtures added after the last B200 run: excluded from the GPU parametrisations unless SCL_TEST_EXPERIMENTAL=1."""
-    import os
-
-    return "asym" in name and os.environ.get("SCL_TEST_EXPERIMENTAL") != "1"

@@ -24,17 +24,29 @@ class EmulatedOps:
         self.round_bf16 = round_bf16
         self.calls = []
 
-    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
+    def cast_bf16(self, x, normalize=False):
         self.calls.append("cast_bf16")
         xf = x.float()
         if normalize:
             xf = torch.nn.functional.normalize(xf, dim=-1)
-        y = xf.to(torch.bfloat16) if self.round_bf16 else xf.clone()
-        y_t = None
-        if want_t:
-            y_t = torch.zeros(x.shape[1], ld_t, dtype=y.dtype)
-            y_t[:, : x.shape[0]] = y.t()
-        return (y if want_rows else None), y_t
+        return xf.to(torch.bfloat16) if self.round_bf16 else xf.clone()
+
+    def check_positives(self, col, q, n_global, rank):
+        self.calls.append("check_positives")
+        b_local = col.shape[0]
+        bad = (col < -1) | (col >= n_global)
+        flag = 0
+        if bool(bad.any()):
+            flag |= 1
+        col_out = torch.where(bad, torch.full_like(col, -1), col)
+        own = torch.arange(b_local, dtype=col.dtype) + rank * b_local
+        if not torch.equal(col_out[:, 0], own):
+            flag |= 2
+        unused = col_out < 0
+        if bool(((col == -1) & (q != 0)).any()):
+            flag |= 4
+        q_out = torch.where(unused, torch.zeros_like(q), q)
+        return col_out, q_out, torch.tensor([flag], dtype=torch.int32)
 
     def prep_scalars(self, logit_scale, cap):
         s = float(logit_scale[0])
@@ -102,23 +114,17 @@ class EmulatedOps:
         return torch.stack([loss, gap, ds, 2 * w * gap]).float()
 
     # ---- composite phases, assembled from the per-op contracts above
-    def prepare(self, image, text, logit_scale, cap, want_img_t, want_txt_t, ld_t, split=False):
+    def prepare(self, image, text, logit_scale, cap, split=False):
         # split (the fp32-accurate mode): the checker keeps the unrounded values in one [rows, D] tensor -- the
         # hi/lo layout is a device detail; what the host logic must get right is which tensor goes where
         self.calls.append("prepare_split" if split else "prepare")
         rb, self.round_bf16 = self.round_bf16, self.round_bf16 and not split
         try:
-            img, img_t = self.cast_bf16(image, want_t=want_img_t and not split, ld_t=ld_t)
-            txt, txt_t = self.cast_bf16(text, want_t=want_txt_t and not split, ld_t=ld_t)
+            img = self.cast_bf16(image)
+            txt = self.cast_bf16(text)
         finally:
             self.round_bf16 = rb
-        return img, txt, img, txt, img_t, txt_t, self.prep_scalars(logit_scale, cap)
-
-    def transpose_split(self, cols_all, d, ld_t):
-        self.calls.append("transpose_split")
-        y_t = torch.zeros(d, ld_t, dtype=cols_all.dtype)
-        y_t[:, : cols_all.shape[0]] = cols_all.t()
-        return y_t
+        return img, txt, img, txt, self.prep_scalars(logit_scale, cap)
 
     def forward_all(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
                     finalize_scalars, want_ranks=False, waits=None, positives=None):
@@ -172,12 +178,11 @@ class EmulatedOps:
             o += n
         return outs
 
-    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+    def bwd_rows(self, x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
         self.calls.append("bwd_rows")
         m, d = x_rows.shape
         n = y_all.shape[0]
-        assert torch.equal(y_all_t[:, :n].float(), y_all.t().float())
         s_eff, s2 = float(scalars[0]), float(scalars[1])
         g = float(grad_out[0]) * mult * c
         xd, yd = x_rows.double(), y_all.double()
@@ -228,11 +233,8 @@ class SplitArithmeticOps(EmulatedOps):
     hi/lo pairs, z = xh.yh + xh.yl + xl.yh, dL/dz split into two bf16 tiles, dX = G1.Yh + G1.Yl + G2.Yh -- so the
     error budget of that scheme can be pinned against the reference goldens without a GPU
     (tests/test_fp32_mode_numerics.py)."""
-    def cast_bf16(self, x, want_rows=True, want_t=False, ld_t=0, normalize=False):
-        y = x.float().clone(); y_t = None
-        if want_t:
-            y_t = torch.zeros(x.shape[1], ld_t); y_t[:, :x.shape[0]] = y.t()
-        return (y if want_rows else None), y_t
+    def cast_bf16(self, x, normalize=False):
+        return x.float().clone()
     def _z(self, x, y):
         xh, xl = _split2(x); yh, yl = _split2(y)
         return (xh @ yh.t() + xh @ yl.t() + xl @ yh.t())   # fp32
@@ -253,7 +255,7 @@ class SplitArithmeticOps(EmulatedOps):
             zz = (xh * yh[cc]).sum(1) + (xh * yl[cc]).sum(1) + (xl * yh[cc]).sum(1)
             zq += torch.where(ok, pos_q[:, t] * zz, torch.zeros_like(zz))
         return torch.stack([m + torch.log2(s0), mu, var, zq], dim=1).float()
-    def bwd_rows(self, x_rows, y_all, y_all_t, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
+    def bwd_rows(self, x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                  b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local=None):
         m, d = x_rows.shape; n = y_all.shape[0]
         s_eff, s2 = float(scalars[0]), float(scalars[1])

@@ -36,29 +36,26 @@ def test_every_declared_symbol_is_exported(lib):
 def test_plans_and_errors_without_gpu(lib):
     from spatial_clip_b200._cuda import SclPlan
 
-    assert lib.scl_abi_version() == 6
+    assert lib.scl_abi_version() == 7
     p = SclPlan()
-    assert lib.scl_fwd_plan(4096, 32768, 512, 0, ctypes.byref(p)) == 0
-    assert p.m_pad == 4096 and p.n_slots == 2 * p.chunks and p.variant == 0 and p.chunks * p.tiles_per_chunk >= 32768 // 256
+    assert lib.scl_fwd_plan(4096, 32768, 512, ctypes.byref(p)) == 0
+    assert p.m_pad == 4096 and p.n_slots == 4 * p.chunks and p.chunks * p.tiles_per_chunk >= 32768 // 256
     assert lib.scl_bwd_plan(300, 300, 512, 0, ctypes.byref(p)) == 0
-    assert p.m_pad == 384 and p.n_pad == 384 and p.d_split == 2
-    assert lib.scl_fwd_plan(128, 128, 96, -1, ctypes.byref(p)) == -2  # D % 64 != 0
-    assert lib.scl_fwd_plan(128, 128, 1024, 0, ctypes.byref(p)) == -2  # D > 512 needs the CTA-pair kernels
-    assert lib.scl_fwd_plan(128, 128, 1024, 1, ctypes.byref(p)) == 0
-    assert lib.scl_bwd_plan(128, 128, 768, 1, ctypes.byref(p)) == 0 and p.d_split == 2
-    assert lib.scl_fwd_plan(128, 128, 640, 1, ctypes.byref(p)) == 0  # the streamed forward takes any D % 64 == 0 ...
-    assert lib.scl_bwd_plan(128, 128, 640, 1, ctypes.byref(p)) == -2  # ... the backward needs D % 256 == 0 beyond 512
-    assert lib.scl_fwd_plan(128, 128, 3 * 1024, 1, ctypes.byref(p)) == 0  # K-concatenated fp32-mode operands
-    assert lib.scl_fwd_plan(128, 128, 3 * 1024 + 64, 1, ctypes.byref(p)) == -2
-    assert lib.scl_bwd_plan_ex(300, 300, 512, 1, 1, ctypes.byref(p)) == 0 and p.split == 1 and p.d_split == 1
-    assert lib.scl_bwd_plan_ex(300, 300, 512, 0, 1, ctypes.byref(p)) == -2  # fp32 mode: CTA-pair kernels only
-    assert lib.scl_bwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0 and p.split == 0
+    assert p.m_pad == 384 and p.n_pad == 512 and p.d_split == 1 and p.split == 0
+    assert lib.scl_fwd_plan(128, 128, 96, ctypes.byref(p)) == -2  # D % 64 != 0
+    assert lib.scl_fwd_plan(128, 128, 1024, ctypes.byref(p)) == 0
+    for d, slices in ((640, 2), (768, 2), (1024, 2), (1152, 3), (1280, 4), (1536, 3)):
+        assert lib.scl_bwd_plan(128, 128, d, 0, ctypes.byref(p)) == 0 and p.d_split == slices, d
+    assert lib.scl_bwd_plan(128, 128, 1600, 0, ctypes.byref(p)) == -2  # beyond 1536
+    assert lib.scl_fwd_plan(128, 128, 3 * 1536, ctypes.byref(p)) == 0  # K-concatenated fp32-mode operands
+    assert lib.scl_fwd_plan(128, 128, 3 * 1536 + 64, ctypes.byref(p)) == -2
+    assert lib.scl_bwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0 and p.split == 1 and p.d_split == 1
     assert b"unsupported shape" in lib.scl_error_string(-2)
-    assert lib.scl_bwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
-    assert p.variant == 1 and p.m_pad == 384 and p.n_pad == 512 and p.d_split == 1
-    assert lib.scl_fwd_plan(300, 300, 512, 1, ctypes.byref(p)) == 0
-    assert p.variant == 1 and p.m_pad == 512
+    assert lib.scl_fwd_plan(300, 300, 512, ctypes.byref(p)) == 0 and p.m_pad == 512
     assert lib.scl_positives_workspace_bytes(1000) >= 2048 * 12
+    # the backward's chunk picker charges every chunk's partial slab: few chunks for a rank of an 8-GPU job
+    assert lib.scl_bwd_plan(4096, 32768, 512, 0, ctypes.byref(p)) == 0 and p.chunks <= 5
+    assert lib.scl_bwd_workspace_bytes(4096, 32768, 512, 9) > 0 and lib.scl_bwd_finish_workspace_bytes(32768, 4096, 9) > 0
 
 
 def test_ctypes_structs_match_the_header(tmp_path):

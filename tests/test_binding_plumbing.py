@@ -10,8 +10,8 @@ import torch
 from spatial_clip_b200 import ClipLoss, SpatialLoss, _cuda, losses
 from spatial_clip_b200.synth import make_spot_batch
 
-HOST_ONLY = {"scl_abi_version", "scl_error_string", "scl_fwd_plan", "scl_bwd_plan", "scl_bwd_plan_ex",
-             "scl_positives_workspace_bytes", "scl_fwd_workspace_bytes", "scl_bwd_workspace_bytes"}
+HOST_ONLY = {"scl_abi_version", "scl_error_string", "scl_fwd_plan", "scl_bwd_plan", "scl_positives_workspace_bytes",
+             "scl_fwd_workspace_bytes", "scl_bwd_workspace_bytes", "scl_bwd_finish_workspace_bytes"}
 
 
 class _CallbackLib:
@@ -39,14 +39,11 @@ class _CallbackLib:
 
 
 class _PlumbingOps(_cuda.CudaOps):
-    def __init__(self, lib, mn_major=False, overlap_gather=False):
+    def __init__(self, lib):
         self.lib = lib
-        self.overlap_gather = overlap_gather
         self._checked = set()
-        self.variant = 1
         self.launches = 0
         self.kernel_events = None
-        self.mn_major = mn_major
 
     def _stream(self, t):
         return 0
@@ -97,11 +94,11 @@ def _step(mod, b, spatial=True, d_dtype=torch.float32):
     return out
 
 
-@pytest.mark.parametrize("mode", ["default", "fp32", "ranks", "mn_major", "bf16_inputs", "timed_kernels", "d768"])
+@pytest.mark.parametrize("mode", ["default", "fp32", "ranks", "bf16_inputs", "timed_kernels", "d768", "d1280"])
 def test_every_mode_reaches_the_library_with_well_formed_calls(plumbing, mode):
-    d = 768 if mode == "d768" else 128
+    d = {"d768": 768, "d1280": 1280}.get(mode, 128)
     b = make_spot_batch(n=300, d=d, k=8, seed=3)
-    ops, lib = plumbing(mn_major=(mode == "mn_major"))
+    ops, lib = plumbing()
     kw = {}
     if mode == "fp32":
         kw["precision"] = "fp32"
@@ -111,7 +108,7 @@ def test_every_mode_reaches_the_library_with_well_formed_calls(plumbing, mode):
                neighbor_alpha_scale=0.5, float32_logits=True)
     mod = SpatialLoss(**cfg, **kw)
     if mode == "timed_kernels":  # bench.py's roofline / developer timing mode: the backward launches go out one by one
-        ops.cycle_buffers = {}
+        ops.kernel_events = {}
         _step(mod, b)
         assert {"scl_bwd_coeffs", "scl_bwd_rows", "scl_bwd_finish"} <= set(lib.calls) and "scl_bwd_dir" not in lib.calls
         return
@@ -119,12 +116,10 @@ def test_every_mode_reaches_the_library_with_well_formed_calls(plumbing, mode):
     calls = lib.calls
     assert calls.count("scl_fwd_all") == 1 and calls.count("scl_bwd_dir") == 2
     if mode == "fp32":
-        assert calls.count("scl_split_bf16") == 2 and calls.count("scl_transpose_split") == 2
+        assert calls.count("scl_split_bf16") == 2
         assert "scl_prepare" not in calls and "scl_cast_bf16" not in calls
     else:
-        assert calls.count("scl_prepare") == 1
-        # single rank: the transposed copies come out of scl_prepare; with the MN-major knob there are none at all
-        assert "scl_cast_bf16" not in calls and "scl_transpose_split" not in calls
+        assert calls.count("scl_prepare") == 1 and "scl_cast_bf16" not in calls  # no transposed copies anywhere
     if mode == "ranks":
         assert mod.last_retrieval_ranks is not None and mod.last_retrieval_ranks.shape == (300,)
     # plain CLIP through the same layer
@@ -153,9 +148,9 @@ def _gloo_worker(rank, world, port, mode, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         _cuda._DeviceGuard = _NoGuard
         lib = _CallbackLib(_cuda.load_library())
-        losses._set_ops_for_testing(_PlumbingOps(lib, mn_major=(mode == "mn_major"), overlap_gather=(mode == "overlap")))
+        losses._set_ops_for_testing(_PlumbingOps(lib))
         b = make_spot_batch(n=256, d=128, k=8, seed=5).rank_slice(rank, world)
-        cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+        cfg = dict(local_loss=True, gather_with_grad=(mode != "local_only"), cap_logit_scale=40.0, temp_reg_weight=0.05,
                    neighbor_alpha_scale=0.5, float32_logits=True)
         _step(SpatialLoss(**cfg, **({"precision": "fp32"} if mode == "fp32" else {})), b)
         q.put((rank, list(lib.calls)))
@@ -165,10 +160,11 @@ def _gloo_worker(rank, world, port, mode, q):
         q.put((rank, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("mode", ["default", "fp32", "mn_major", "overlap"])
+@pytest.mark.parametrize("mode", ["default", "fp32", "local_only"])
 def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
-    """world_size 2: gathered operands, the single statistics-record exchange (scl_unpack_records with its pointer
-    tables) and, for W > 1, the transposed copies made in backward."""
+    """world_size 2: gathered operands, one scl_fwd_all call per forward phase and the single statistics-record
+    exchange (scl_unpack_records with its pointer tables) -- none at all when no other rank's rows reach the local
+    features (local_loss without a differentiable gather, like the reference's backward)."""
     import socket
 
     import torch.multiprocessing as mp
@@ -191,20 +187,15 @@ def test_two_ranks_over_gloo_issue_the_same_call_sequence(mode):
         assert isinstance(got[r], list), got[r]
     assert got[0] == got[1], "ranks must issue identical call sequences (collective order)"
     calls = got[0]
-    # overlapped exchanges: one scl_fwd_all call per phase (soft targets / image-rows pass / text-rows pass)
-    assert calls.count("scl_fwd_all") == (3 if mode == "overlap" else 1)
-    assert calls.count("scl_unpack_records") == 1 and calls.count("scl_bwd_dir") == 2
-    if mode == "fp32":
-        assert calls.count("scl_transpose_split") == 2
-    elif mode == "mn_major":
-        assert "scl_cast_bf16" not in calls
-    else:
-        assert calls.count("scl_cast_bf16") == 2  # transposed copies of the two gathered operands
+    # exchanges in flight: one scl_fwd_all call per phase (soft targets / image-rows pass / text-rows pass)
+    assert calls.count("scl_fwd_all") == 3 and calls.count("scl_bwd_dir") == 2
+    assert calls.count("scl_unpack_records") == (0 if mode == "local_only" else 1)
+    assert "scl_cast_bf16" not in calls
 
 
 def test_precomputed_columns_skip_the_builder_phase(plumbing):
-    """SpatialLossFromColumns: one scl_fwd_all call with phases = 6 (both similarity passes, no soft-target builder),
-    the caller's int32 / fp32 lists go to the library as they are."""
+    """SpatialLossFromColumns: one scl_fwd_all call with phases = 6 (both similarity passes, no soft-target builder);
+    the caller's int32 / fp32 lists reach it through scl_check_positives."""
     from spatial_clip_b200 import SpatialLossFromColumns
     from spatial_clip_b200.positives import resolve_positive_columns
 
@@ -217,6 +208,7 @@ def test_precomputed_columns_skip_the_builder_phase(plumbing):
     mod(img, txt, torch.tensor(30.0, requires_grad=True), positive_columns=col, positive_probs=q,
         positive_weights=w)["contrastive_loss"].backward()
     assert lib.calls.count("scl_fwd_all") == 1 and lib.fwd_phases == [6] and lib.calls.count("scl_bwd_dir") == 2
+    assert lib.calls.count("scl_check_positives") == 1
     assert img.grad.shape == img.shape and mod.last_positives[0].dtype == torch.int32
     # the ordinary route asks for everything in one call
     lib.calls.clear()

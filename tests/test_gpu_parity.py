@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, text_ids_for, unverified_on_gpu
+from conftest import golden_names, load_golden, text_ids_for
 from oracle.contrastive_oracle import (clip_loss_oracle, dense_labels, soft_label_triples,
                                        spatial_loss_oracle)
 from spatial_clip_b200.synth import make_spot_batch
@@ -15,23 +15,17 @@ LOG2E = 1.4426950408889634
 LN2 = 0.6931471805599453
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["cta1", "cta2"])
-def ops(request):
-    """CudaOps with the single-CTA (cta_group::1) or CTA-pair (cta_group::2) tensor-core kernels; the
-    modules under test use the same object."""
-    import os
-
+@pytest.fixture(scope="module")
+def ops():
+    """The CudaOps object the modules under test use too."""
     from spatial_clip_b200 import losses
     from spatial_clip_b200._cuda import CudaOps
 
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     o = CudaOps()
-    o.variant = request.param
-    os.environ["SCL_VARIANT"] = str(request.param)  # inherited by the spawned rank workers
     prev = losses._set_ops_for_testing(o)
     yield o
     losses._set_ops_for_testing(prev)
-    os.environ.pop("SCL_VARIANT", None)
 
 
 def _bf16_pair(m, n, d, seed):
@@ -75,8 +69,7 @@ def test_row_statistics(ops, m, n, d, s):
 
 
 # ---------------------------------------------------------------- layer 3: integer path, bit exact
-@pytest.mark.parametrize("name", [n for n in golden_names("spatial", world=1)
-                                  if "bias" not in n and "legacy" not in n and not unverified_on_gpu(n)])
+@pytest.mark.parametrize("name", [n for n in golden_names("spatial", world=1) if "bias" not in n and "legacy" not in n])
 def test_positive_lists_bit_exact_vs_reference_labels(ops, name):
     meta, gold = load_golden(name)
     if "labels_i_t" not in gold:
@@ -147,16 +140,14 @@ def test_bwd_rows_matches_dense_formula(ops, m, n, d):
     oq = torch.zeros((n, 1), device="cuda")
     gaps = torch.tensor([0.3], device="cuda")
     go = torch.tensor([1.7], device="cuda")
-    ld_t = (n + 7) // 8 * 8
-    _, y_t = ops.cast_bf16(y, want_rows=False, want_t=True, ld_t=ld_t)
     args = (rs, cs, col, q, ocol, oq, max(m, n), 0, gaps, scal, go, 0.5 / m, 0.05, 1.0, 2, torch.float32)
-    got = ops.bwd_rows(x, y, y_t, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
+    got = ops.bwd_rows(x, y, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
     torch.cuda.synchronize()
     cpu = [a.cpu() if torch.is_tensor(a) else a for a in args]
-    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), y_t.cpu(), *cpu)
+    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), *cpu)
     err = (got.cpu() - want).abs().max().item()
     ref = want.abs().max().item()
-    assert err <= 1.2e-2 * ref, f"bwd_rows err {err} vs max {ref}"  # G is rounded to bf16 for the 2nd GEMM
+    assert err <= 5e-3 * ref, f"bwd_rows err {err} vs max {ref}"  # G is rounded to bf16 for the 2nd GEMM
 
 
 # ---------------------------------------------------------------- layer 5: the modules, vs the reference
@@ -168,7 +159,13 @@ def _module_run(meta, dtype=torch.float32):
     txt = b.text_features.cuda().to(dtype).requires_grad_(True)
     s = torch.tensor(float(meta["scale"]), device="cuda", requires_grad=True)
     c = dict(meta["ctor"])
-    if meta["kind"] == "spatial":
+    if meta["kind"] == "legacy":  # positional order of open_clip_train, bare-tensor return
+        from spatial_clip_b200 import GlobalMappingMultiPositiveClipLoss
+
+        mod = GlobalMappingMultiPositiveClipLoss(**c)
+        out = {"contrastive_loss": mod(img, txt, b.tile_ids.cuda(), text_ids_for(meta, b).cuda(),
+                                       b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda(), s)}
+    elif meta["kind"] == "spatial":
         mod = SpatialLoss(**c)
         out = mod(img, txt, s, b.tile_ids.cuda(), text_ids_for(meta, b).cuda(), b.neighbor_tile_ids.cuda(),
                   b.neighbor_alphas.cuda())
@@ -185,7 +182,7 @@ def _oracle_on_bf16_inputs(meta, b):
     img = b.image_features.to(torch.bfloat16).float().numpy()
     txt = b.text_features.to(torch.bfloat16).float().numpy()
     c = meta["ctor"]
-    if meta["kind"] == "spatial":
+    if meta["kind"] in ("spatial", "legacy"):
         return spatial_loss_oracle(img, txt, meta["scale"], b.tile_ids.numpy(), text_ids_for(meta, b).numpy(),
                                    b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy(), 1,
                                    c.get("cap_logit_scale"), c.get("temp_reg_weight", 0.0),
@@ -193,13 +190,17 @@ def _oracle_on_bf16_inputs(meta, b):
     return clip_loss_oracle(img, txt, meta["scale"])
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names(world=1) if "legacy" not in n and not unverified_on_gpu(n)])
+@pytest.mark.parametrize("name", golden_names(world=1))
 def test_modules_match_reference(ops, name):
     """Gate (SURVEY 8d "parity gates", bf16 mode): against the oracle evaluated in fp64 on the SAME bf16-rounded
-    inputs -- loss rel 2e-5 (+ the fp32-LSE floor), d_scale rel 1e-3, grads 1.2e-2 of ||grad||_inf (dL/dz is
-    rounded to bf16 for the second GEMM).  Informational second check against the reference's fp32 goldens
-    (un-rounded fp32 inputs): loss rel 1e-3, grads 3e-2 of ||grad||_inf."""
+    inputs -- loss rel 2e-5 (+ the fp32-LSE floor), d_scale rel 1e-3, grads 5e-3 of ||grad||_inf (dL/dz is
+    rounded to bf16 for the second GEMM; measured 1.4e-3 .. 2.5e-3).  Second check against the reference's fp32
+    goldens (un-rounded fp32 inputs): loss rel 1e-3, grads 3e-2 of ||grad||_inf.  A saturated fixture (loss ~ 0,
+    gradients at rounding level) cannot fail a relative gate meaningfully: it is checked in absolute terms instead
+    (|grad| itself below the floor that the bf16 rounding of dL/dz allows)."""
     meta, gold = load_golden(name)
+    if name.startswith("legacy"):  # same arithmetic through the open_clip_train positional signature
+        meta = dict(meta, kind="legacy")
     b, loss, gi, gt, ds = _module_run(meta)
     scale = meta["scale"]
     orc = _oracle_on_bf16_inputs(meta, b)
@@ -210,8 +211,12 @@ def test_modules_match_reference(ops, name):
     print(name, report)
     assert abs(loss - r0.loss) <= 2e-5 * abs(r0.loss) + 2e-6 * scale, report
     assert abs(ds - r0.d_scale) <= 1e-3 * abs(r0.d_scale) + 2e-6, report
+    floor = 3e-6 * scale * 0.5 / len(orc.d_image)  # rounding level of dL/dz (bf16) x |Y| for one row
     for got, ref in ((gi, orc.d_image), (gt, orc.d_text)):
-        assert np.abs(got - ref).max() <= 1.2e-2 * np.abs(ref).max() + 3e-6 * scale * 0.5 / len(ref), report
+        if np.abs(ref).max() <= 4 * floor:  # saturated fixture (clip_n128_w1_s100): nothing relative to compare
+            assert np.abs(got).max() <= 8 * floor, report
+            continue
+        assert np.abs(got - ref).max() <= 5e-3 * np.abs(ref).max() + floor, report
     assert abs(loss - gold["loss"][0]) <= 1e-3 * abs(gold["loss"][0]) + 2e-6 * scale, report
     for got, ref in ((gi, gold["d_image"]), (gt, gold["d_text"])):
         assert np.abs(got - ref).max() <= 3e-2 * np.abs(ref).max() + 3e-6 * scale * 0.5 / len(ref), report
@@ -260,7 +265,7 @@ def test_clip_mid_size_vs_dense_checker(ops, n, d, s):
     assert abs(float(loss) - float(want_loss)) <= 2e-5 * float(want_loss) + 2e-6 * s
     assert abs(float(sc.grad) - float(wds)) <= 2e-3 * abs(float(wds)) + 1e-6
     for got, ref in ((img.grad, wi), (txt.grad, wt)):
-        assert (got.double() - ref).abs().max().item() <= 1.2e-2 * ref.abs().max().item()
+        assert (got.double() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
     # Euler identity: sum_i <x_i, dL/dx_i> = s * dL/ds for both modalities (size independent)
     e_i = (img.grad.double() * img.detach().double()).sum().item()
     e_t = (txt.grad.double() * txt.detach().double()).sum().item()
@@ -280,7 +285,7 @@ def test_full_size_identities_n32768(ops):
     mod = SpatialLoss(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.0,
                       neighbor_alpha_scale=0.5, float32_logits=True)
     ids = b.tile_ids.cuda()
-    loss = mod(img, txt, sc, ids, ids, b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())["contrastive_loss"]
+    loss = mod(img, txt, sc, ids, ids.clone(), b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())["contrastive_loss"]
     loss.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(loss) and torch.isfinite(img.grad).all() and torch.isfinite(txt.grad).all()
@@ -309,6 +314,44 @@ def test_full_size_identities_n32768(ops):
         zq += torch.where(c >= 0, q[rows, t].double() * zz, torch.zeros_like(zz))
     per_row = lse - s_eff * zq  # image-direction loss terms of the sampled rows
     assert torch.isfinite(per_row).all() and (per_row > -1e-6).all()
+
+
+# ---------------------------------------------------------------- BASELINE sizes: blockwise fp64 oracle
+@pytest.mark.parametrize("n,same_ids", [(16384, True), (32768, True), (16384, False)])
+def test_baseline_size_loss_and_sampled_gradients(ops, n, same_ids):
+    """BASELINE configs[2] (N=16384, K=8) and the metric's batch (N=32768) with the shipped hyper-parameters
+    (cap 40, temperature regulariser 0.05, alpha scale 0.5): loss, d logit_scale and 64 sampled rows of dImage / dGene
+    against the blockwise fp64 oracle (oracle/blockwise_oracle.py) on the same bf16-rounded inputs.
+    Gates: loss rel 2e-5, d_scale rel 1e-3, sampled gradient rows 5e-3 of the largest sampled gradient entry."""
+    from oracle.blockwise_oracle import blockwise_oracle, sample_rows_for
+    from spatial_clip_b200 import SpatialLoss
+    from spatial_clip_b200.synth import shuffled_text_ids
+
+    d, k = 512, 8
+    b = make_spot_batch(n=n, d=d, k=k, seed=1004)
+    tids = b.tile_ids if same_ids else shuffled_text_ids(b.tile_ids, 77)
+    img = b.image_features.cuda().requires_grad_(True)
+    txt = b.text_features.cuda().requires_grad_(True)
+    sc = torch.tensor(55.0, device="cuda", requires_grad=True)
+    cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+               neighbor_alpha_scale=0.5, float32_logits=True)
+    loss = SpatialLoss(**cfg)(img, txt, sc, b.tile_ids.cuda(), tids.cuda(), b.neighbor_tile_ids.cuda(),
+                              b.neighbor_alphas.cuda())["contrastive_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    rows = sample_rows_for(n, 8, 8, seed=n)
+    ref = blockwise_oracle(b.image_features.bfloat16().float().numpy(), b.text_features.bfloat16().float().numpy(),
+                           55.0, b.tile_ids.numpy(), tids.numpy(), b.neighbor_tile_ids.numpy(),
+                           b.neighbor_alphas.numpy(), 1, 40.0, 0.05, 0.5, True, True, rows)
+    gi = img.grad[rows].double().cpu().numpy()
+    gt = txt.grad[rows].double().cpu().numpy()
+    rep = dict(loss=(float(loss), ref.loss[0]), ds=(float(sc.grad), ref.d_scale[0]),
+               gi=np.abs(gi - ref.d_image_rows).max() / np.abs(ref.d_image_rows).max(),
+               gt=np.abs(gt - ref.d_text_rows).max() / np.abs(ref.d_text_rows).max())
+    print("baseline-size parity", n, same_ids, rep)
+    assert abs(float(loss) - ref.loss[0]) <= 2e-5 * abs(ref.loss[0]), rep
+    assert abs(float(sc.grad) - ref.d_scale[0]) <= 1e-3 * abs(ref.d_scale[0]), rep
+    assert rep["gi"] <= 5e-3 and rep["gt"] <= 5e-3, rep
 
 
 # ---------------------------------------------------------------- ranks sharing this GPU (gloo transport)
@@ -389,17 +432,10 @@ def test_multi_rank_on_one_gpu(ops, name):
 # ---------------------------------------------------------------- wide embeddings (ViT-L / ViT-H: D = 768, 1024)
 @pytest.mark.parametrize("m,n,d", [(300, 700, 768), (257, 1025, 1024)])
 def test_wide_embeddings_kernels(ops, m, n, d):
-    """D > 512: streamed-X forward, two-slice backward (CTA-pair kernels only)."""
+    """D > 512: streamed-X forward, two-slice backward."""
     from dense_checker import row_stats
     from emulated_ops import EmulatedOps
 
-    if ops.variant == 0:
-        from spatial_clip_b200._cuda import SclError
-
-        x, y = _bf16_pair(64, 64, d, seed=1)
-        with pytest.raises(SclError):
-            ops.fwd_rowstats(x, y, ops.prep_scalars(torch.tensor([20.0], device="cuda"), None))
-        return
     x, y = _bf16_pair(m, n, d, seed=m + n + d)
     s = 30.0
     scal = ops.prep_scalars(torch.tensor([s], device="cuda"), None)
@@ -421,19 +457,15 @@ def test_wide_embeddings_kernels(ops, m, n, d):
     oq = torch.zeros((n, 1), device="cuda")
     gaps = torch.tensor([0.2], device="cuda")
     go = torch.tensor([1.3], device="cuda")
-    ld_t = (n + 7) // 8 * 8
-    _, y_t = ops.cast_bf16(y, want_rows=False, want_t=True, ld_t=ld_t)
     args = (rs, cs, col, q, ocol, oq, max(m, n), 0, gaps, scal, go, 0.5 / m, 0.05, 1.0, 2, torch.float32)
-    got = ops.bwd_rows(x, y, y_t, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
+    got = ops.bwd_rows(x, y, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
     torch.cuda.synchronize()
-    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), y_t.cpu(), *[a.cpu() if torch.is_tensor(a) else a for a in args])
-    assert (got.cpu() - want).abs().max().item() <= 1.2e-2 * want.abs().max().item()
+    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), *[a.cpu() if torch.is_tensor(a) else a for a in args])
+    assert (got.cpu() - want).abs().max().item() <= 5e-3 * want.abs().max().item()
 
 
-@pytest.mark.parametrize("d", [768, 1024])
+@pytest.mark.parametrize("d", [640, 768, 1024, 1280])
 def test_wide_embeddings_module_vs_oracle(ops, d):
-    if ops.variant == 0:
-        pytest.skip("single-CTA kernels stop at D = 512")
     from spatial_clip_b200 import SpatialLoss
 
     gen = dict(n=300, d=d, k=8, seed=4000 + d, dup_frac=0.01, self_loops=True)
@@ -455,4 +487,44 @@ def test_wide_embeddings_module_vs_oracle(ops, d):
     assert abs(float(loss.detach()) - r0.loss) <= 2e-5 * abs(r0.loss) + 1e-4
     assert abs(float(s.grad) - r0.d_scale) <= 1e-3 * abs(r0.d_scale) + 2e-6
     for got, ref in ((img.grad.cpu().numpy(), orc.d_image), (txt.grad.cpu().numpy(), orc.d_text)):
-        assert np.abs(got - ref).max() <= 1.2e-2 * np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 5e-3 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------- run-to-run determinism
+def test_backward_is_bitwise_reproducible(ops):
+    """No atomics anywhere on the gradient path: chunk partials are summed in chunk order and the opposite-direction
+    soft-target terms in ascending entry order (bwd_gather), so two runs give bit-identical results -- also with
+    duplicate tile ids and hub rows that many rows name as a neighbour."""
+    from spatial_clip_b200 import SpatialLoss
+
+    b = make_spot_batch(n=4096, d=256, k=8, seed=99, dup_frac=0.05, self_loops=True)
+    nbr = b.neighbor_tile_ids.clone()
+    alpha = b.neighbor_alphas.clone()
+    nbr[::3, 0] = b.tile_ids[7]  # a hub: ~1365 rows list row 7 (bucket > 32 entries: the selection path)
+    alpha[::3, 0] = 0.2
+    cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+               neighbor_alpha_scale=0.5, float32_logits=True)
+
+    def run():
+        img = b.image_features.cuda().requires_grad_(True)
+        txt = b.text_features.cuda().requires_grad_(True)
+        s = torch.tensor(55.0, device="cuda", requires_grad=True)
+        ids = b.tile_ids.cuda()
+        loss = SpatialLoss(**cfg)(img, txt, s, ids, ids.clone(), nbr.cuda(), alpha.cuda())["contrastive_loss"]
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.detach().clone(), img.grad.clone(), txt.grad.clone(), s.grad.clone()
+
+    first = run()
+    for _ in range(2):
+        again = run()
+        for a, c in zip(first, again):
+            assert torch.equal(a, c)
+    # and the hub row's gradient is right (dense fp64 oracle on the bf16-rounded inputs)
+    orc = spatial_loss_oracle(b.image_features.bfloat16().float().numpy(), b.text_features.bfloat16().float().numpy(),
+                              55.0, b.tile_ids.numpy(), b.tile_ids.numpy(), nbr.numpy(), alpha.numpy(), 1, 40.0, 0.05, 0.5)
+    gi = first[1].cpu().numpy()
+    assert np.abs(gi - orc.d_image).max() <= 5e-3 * np.abs(orc.d_image).max()
+    assert np.abs(gi[7] - orc.d_image[7]).max() <= 5e-3 * np.abs(orc.d_image[7]).max()
+    gt = first[2].cpu().numpy()
+    assert np.abs(gt - orc.d_text).max() <= 5e-3 * np.abs(orc.d_text).max()

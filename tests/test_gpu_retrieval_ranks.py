@@ -1,17 +1,12 @@
 """GPU parity of the in-pass retrieval ranks: the counts of fwd_rowstats_pair_kernel<1> against the
 reference metric's logits-matmul + topk on the same bf16-rounded features.
-
-EXPERIMENTAL: written after the round's GPU budget was spent; skipped unless SCL_TEST_EXPERIMENTAL=1."""
-import os
-
+"""
 import pytest
 import torch
 
 from spatial_clip_b200.synth import make_spot_batch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SCL_TEST_EXPERIMENTAL") != "1",
-                                 reason="in-pass retrieval ranks not yet run on a B200 (set SCL_TEST_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -20,7 +15,6 @@ def ops():
     from spatial_clip_b200._cuda import CudaOps
 
     o = CudaOps()
-    o.variant = 1
     prev = losses._set_ops_for_testing(o)
     yield o
     losses._set_ops_for_testing(prev)

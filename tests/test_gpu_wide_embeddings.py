@@ -20,9 +20,7 @@ LN2 = 0.6931471805599453
 def ops():
     from spatial_clip_b200._cuda import CudaOps
 
-    o = CudaOps()
-    o.variant = 1
-    return o
+    return CudaOps()
 
 
 @pytest.mark.parametrize("m,n,d", [(300, 700, 640), (257, 1025, 1152), (130, 520, 1280), (300, 300, 1536)])
@@ -52,10 +50,8 @@ def test_wider_embeddings_kernels(ops, m, n, d):
     oq = torch.zeros((n, 1), device="cuda")
     gaps = torch.tensor([0.2], device="cuda")
     go = torch.tensor([1.3], device="cuda")
-    ld_t = (n + 7) // 8 * 8
-    _, y_t = ops.cast_bf16(y, want_rows=False, want_t=True, ld_t=ld_t)
     args = (rs, cs, col, q, ocol, oq, max(m, n), 0, gaps, scal, go, 0.5 / m, 0.05, 1.0, 2, torch.float32)
-    got = ops.bwd_rows(x, y, y_t, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
+    got = ops.bwd_rows(x, y, *args, opp_q_local=torch.zeros((m, 1), device="cuda"))
     torch.cuda.synchronize()
-    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), y_t.cpu(), *[a.cpu() if torch.is_tensor(a) else a for a in args])
-    assert (got.cpu() - want).abs().max().item() <= 1.2e-2 * want.abs().max().item()
+    want = EmulatedOps().bwd_rows(x.cpu(), y.cpu(), *[a.cpu() if torch.is_tensor(a) else a for a in args])
+    assert (got.cpu() - want).abs().max().item() <= 5e-3 * want.abs().max().item()

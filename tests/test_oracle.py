@@ -119,3 +119,41 @@ def test_torch_port_matches_reference_goldens():
     loss = clip_rank_step(img, txt, img, txt, s, 0)
     np.testing.assert_allclose(float(loss), gold["loss"][0], rtol=2e-6)
     assert np.abs(img.grad.numpy() - gold["d_image"]).max() <= 1e-5 * np.abs(gold["d_image"]).max()
+
+
+# ---------------------------------------------------------------- the blockwise (large-N) oracle
+@pytest.mark.parametrize("name", [n for n in golden_names("spatial") if "legacy" not in n])
+def test_blockwise_oracle_matches_reference_goldens(name):
+    """oracle/blockwise_oracle.py (the checker of the BASELINE-size GPU tests and of bench.py's parity block) against
+    the reference's own outputs: per-rank loss / d_scale and a sample of gradient rows, every flag combination."""
+    from oracle.blockwise_oracle import blockwise_oracle, sample_rows_for
+
+    meta, gold = load_golden(name)
+    img, txt, ids, nbr, alpha = _inputs(meta)
+    c = meta["ctor"]
+    world = meta["world"]
+    rows = sample_rows_for(img.shape[0], world, 5, seed=3)
+    res = blockwise_oracle(img, txt, meta["scale"], ids, _text_ids(meta), nbr, alpha, world_size=world,
+                           cap_logit_scale=c.get("cap_logit_scale"), temp_reg_weight=c.get("temp_reg_weight", 0.0),
+                           neighbor_alpha_scale=c.get("neighbor_alpha_scale", 1.0), local_loss=c["local_loss"],
+                           gather_with_grad=c["gather_with_grad"], sample_rows=rows, block=48)
+    np.testing.assert_allclose(res.loss, gold["loss"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(res.d_scale, gold["d_scale"], rtol=2e-4, atol=2e-6)
+    assert np.abs(res.d_image_rows - gold["d_image"][rows]).max() <= 2e-5 * np.abs(gold["d_image"]).max() + 1e-9
+    assert np.abs(res.d_text_rows - gold["d_text"][rows]).max() <= 2e-5 * np.abs(gold["d_text"]).max() + 1e-9
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("clip") if "ll1" in n or "_w1_" in n or "n300" in n])
+def test_blockwise_oracle_clip_matches_reference_goldens(name):
+    from oracle.blockwise_oracle import blockwise_oracle, sample_rows_for
+
+    meta, gold = load_golden(name)
+    img, txt, _, _, _ = _inputs(meta)
+    c = meta["ctor"]
+    world = meta["world"]
+    rows = sample_rows_for(img.shape[0], world, 5, seed=4)
+    res = blockwise_oracle(img, txt, meta["scale"], None, None, None, None, world_size=world, local_loss=True,
+                           gather_with_grad=c.get("gather_with_grad", False), sample_rows=rows, block=40, kind="clip")
+    np.testing.assert_allclose(res.loss, gold["loss"], rtol=2e-6, atol=2e-6)
+    assert np.abs(res.d_image_rows - gold["d_image"][rows]).max() <= 2e-5 * np.abs(gold["d_image"]).max() + 1e-9
+    assert np.abs(res.d_text_rows - gold["d_text"][rows]).max() <= 2e-5 * np.abs(gold["d_text"]).max() + 1e-9

@@ -153,3 +153,41 @@ def test_collate_helper_and_argument_checks():
     with pytest.raises(ValueError):
         SpatialLossFromColumns()(b.image_features, b.text_features, torch.tensor(10.0),
                                  positive_columns=out["positive_columns"][:5], positive_probs=out["positive_probs"])
+
+
+def test_caller_supplied_lists_are_validated():
+    """Lists from outside the library: out-of-range columns, a slot 0 that is not the row's own column
+    (e.g. rank 0's columns used on another rank) and weight on unused slots raise instead of reaching the kernels."""
+    b = make_spot_batch(n=16, d=64, k=4, seed=13)
+    col, w, q = resolve_positive_columns(b.tile_ids, b.neighbor_tile_ids, b.neighbor_alphas, 0.5)
+    prev = losses._set_ops_for_testing(EmulatedOps(round_bf16=False))
+    try:
+        def run(c, p, **kw):
+            return SpatialLossFromColumns(**kw)(b.image_features, b.text_features, torch.tensor(10.0),
+                                                positive_columns=c, positive_probs=p)
+        run(col, q)  # the producer's own output is accepted
+        bad = col.clone()
+        bad[3, 1] = 16  # == N: one past the last column
+        with pytest.raises(ValueError, match="outside"):
+            run(bad, q)
+        with pytest.raises(ValueError, match="own column"):
+            run(col.roll(1, 0), q)  # lists of other rows (what a wrong rank offset produces)
+        bad_q = q.clone()
+        bad_q[col < 0] = 0.25
+        with pytest.raises(ValueError, match="unused slot"):
+            run(col, bad_q)
+    finally:
+        losses._set_ops_for_testing(prev)
+
+
+def test_collate_requires_global_ids_when_distributed(monkeypatch):
+    import spatial_clip_b200.positives as P
+
+    b = make_spot_batch(n=8, d=64, k=2, seed=3)
+    batch = dict(text_tile_ids=b.tile_ids, neighbor_tile_ids=b.neighbor_tile_ids, neighbor_alphas=b.neighbor_alphas)
+    monkeypatch.setattr(P.dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(P.dist, "get_world_size", lambda: 2)
+    with pytest.raises(ValueError, match="all_tile_ids"):
+        collate_positive_columns(batch, 0.5)
+    out = collate_positive_columns(batch, 0.5, all_tile_ids=torch.cat([b.tile_ids, b.tile_ids + 1000]), rank=1)
+    assert torch.equal(out["positive_columns"][:, 0], torch.arange(8, 16, dtype=torch.int32))

@@ -5,7 +5,7 @@ argument plumbing and assertions of tests that cannot run here are at least exer
 Only tests that go through the module API (not raw kernel entry points) can pass this way, and not the multi-rank
 ones (their spawned workers do not inherit the stand-ins): deselect those with -k "not multi_rank".
 
-    SCL_TEST_EXPERIMENTAL=1 python tools/dryrun_gpu_tests.py tests/test_gpu_positive_columns.py [-k expr]
+    python tools/dryrun_gpu_tests.py tests/test_gpu_positive_columns.py [-k expr]
 """
 import sys
 from pathlib import Path
@@ -36,8 +36,6 @@ torch.tensor, torch.zeros, torch.full, torch.empty = map(_cpu, (_real_tensor, _r
 
 
 class DryOps(EmulatedOps):
-    variant = 1
-
     def __init__(self):
         super().__init__(round_bf16=True)
 
