@@ -3,7 +3,7 @@
 
 The reference (Biogod2020/Spatial-Clip) is pure Python, so the analogue of "compile the reference's few source files
 into oracle/_ref/*.so" is ``py_compile``: the three files on the hot path are compiled WHERE THEY LIE under
-/root/reference into ``.pyc`` files under ``oracle/_ref/`` (git-ignored, not gpurun-ignored: the bytecode travels to
+/root/reference into bytecode files (``.bin``: a ``*.pyc`` pattern is commonly excluded when trees are copied) under ``oracle/_ref/`` (git-ignored, not gpurun-ignored: the bytecode travels to
 the GPU box like our own built ``.so``; no reference source is copied into the repository).  ``oracle/ref_loader.py``
 imports them behind a stub ``open_clip`` package (the real ``open_clip/__init__`` needs ftfy / timm, absent here).
 
@@ -31,14 +31,14 @@ SOURCES = {
 def make_ref(verbose: bool = False) -> bool:
     """Returns True when oracle/_ref/ holds the compiled reference modules afterwards."""
     if not REF.exists():
-        return all((OUT / f"{name}.pyc").exists() for name in SOURCES)
+        return all((OUT / f"{name}.bin").exists() for name in SOURCES)
     OUT.mkdir(exist_ok=True)
     for name, rel in SOURCES.items():
         src = REF / rel
-        py_compile.compile(str(src), cfile=str(OUT / f"{name}.pyc"), dfile=f"<reference>/{rel}", doraise=True,
+        py_compile.compile(str(src), cfile=str(OUT / f"{name}.bin"), dfile=f"<reference>/{rel}", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
         if verbose:
-            print(f"compiled {src} -> {OUT / (name + '.pyc')}")
+            print(f"compiled {src} -> {OUT / (name + '.bin')}")
     (OUT / "PYTHON_VERSION").write_text("%d.%d\n" % sys.version_info[:2])
     return True
 

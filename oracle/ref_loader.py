@@ -20,7 +20,7 @@ _CACHE = None
 
 def available() -> bool:
     ver = REF_DIR / "PYTHON_VERSION"
-    return (REF_DIR / "components_losses.pyc").exists() and ver.exists() and \
+    return (REF_DIR / "components_losses.bin").exists() and ver.exists() and \
         ver.read_text().strip() == "%d.%d" % sys.version_info[:2]
 
 
@@ -45,11 +45,11 @@ def load_reference():
     pkg.__path__ = []
     sys.modules["open_clip"] = pkg
     try:
-        oc_loss = _load("open_clip.loss", "open_clip_loss.pyc")
+        oc_loss = _load("open_clip.loss", "open_clip_loss.bin")
         pkg.loss = oc_loss
         pkg.ClipLoss = oc_loss.ClipLoss
-        comp = _load("scl_reference_components_losses", "components_losses.pyc")
-        legacy = _load("scl_reference_legacy_spatial_loss", "legacy_spatial_loss.pyc")
+        comp = _load("scl_reference_components_losses", "components_losses.bin")
+        legacy = _load("scl_reference_legacy_spatial_loss", "legacy_spatial_loss.bin")
     finally:
         if had is not None:
             sys.modules["open_clip"] = had

@@ -350,6 +350,9 @@ class CudaOps:
         positives = (col, w, q) int32 / fp32 / fp32 [B_l, K+1] of the image rows (+ the same three of the text rows):
         soft targets resolved on the data side (already passed through check_positives); the builder phase is
         skipped."""
+        if self.kernel_events is not None and not want_ranks:  # bench.py roofline: time the tensor-core launches
+            return self._forward_all_unfused(img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k,
+                                             alpha_scale, c, w, finalize_scalars, waits, positives)
         st = self._stream(img_l)
         n, d = img_all.shape
         kp1 = k + 1
@@ -405,6 +408,33 @@ class CudaOps:
         built = 0 if positives is not None else (3 if k > 0 else 1) * (1 if same else 2)
         self.launches += built + 5 + (2 if want_ranks else 0)
         return (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks
+
+    def _forward_all_unfused(self, img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, alpha_scale, c, w,
+                             finalize_scalars, waits, positives):
+        """The same sequence as scl_fwd_all, one C-ABI call per launch, so that CUDA events can bracket the two
+        tensor-core passes (kernel_events mode only)."""
+        wait_ids, wait_txt, wait_img = waits if waits is not None else (None, None, None)
+        if wait_ids is not None:
+            wait_ids()
+        if positives is not None:
+            it = tuple(positives[:3])
+            ti = tuple(positives[3:6]) if len(positives) >= 6 else it
+        elif ids is None:
+            it = ti = self.build_positives(None, None, None, b_local, 0, 1.0, rank, img_l)
+        else:
+            it = self.build_positives(ids[1], ids[2], ids[3], b_local, k, alpha_scale, rank, img_l)
+            ti = it if ids[4] else self.build_positives(ids[0], ids[2], ids[3], b_local, k, alpha_scale, rank, img_l)
+        if wait_txt is not None:
+            wait_txt()
+        part, plan = self.fwd_rowstats(img_l, txt_all, scalars)
+        stats_i = self.row_finalize(part, plan, img_l, txt_all, it[0], it[2])
+        if wait_img is not None:
+            wait_img()
+        part, plan = self.fwd_rowstats(txt_l, img_all, scalars)
+        stats_t = self.row_finalize(part, plan, txt_l, img_all, ti[0], ti[2])
+        sums6 = self.reduce_rows(stats_i, stats_t, scalars)
+        out4 = self.loss_scalars(sums6, scalars, c, w) if finalize_scalars else self.empty((4,), torch.float32, img_l)
+        return it, ti, stats_i, stats_t, sums6, out4, None
 
     def backward_dir(self, x_rows, y_all, row_stats, col_stats, pos_col, pos_q, opp_col_all, opp_q_all,
                      b_local, rank, gaps, scalars, grad_out, c, w, mult, col_mode, out_dtype, opp_q_local, split=False):

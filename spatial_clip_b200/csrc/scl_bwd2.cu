@@ -26,12 +26,15 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-#ifndef SCL_B2_STAGES
-#define SCL_B2_STAGES 3
+#ifndef SCL_B2_SLOTS
+#define SCL_B2_SLOTS 7
 #endif
-constexpr int kB2Stages = SCL_B2_STAGES;  // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
+// TMA ring: 16 KB slots, one full / empty barrier pair per slot.  The MMA thread consumes them two at a time (8 MMAs
+// per pair of waits) and releases each slot right behind its own 4 MMAs.  Seven slots are what fits next to the
+// resident X block (64 KB), the G tile (32 KB) and the coefficients (8 KB) in 227 KB; measured (tools/bwd_lab.py):
+// 4 slots 2.29 ms, 6 slots 1.93 ms per launch at N = 32768 -- the kernel is sensitive to the bytes in flight.
+constexpr int kB2Slots = SCL_B2_SLOTS;
 constexpr int kB2SlotBytes = 16384;
-constexpr int kB2StageBytes = 2 * kB2SlotBytes;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
 constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
 constexpr int kB2GBytes = 4 * kB2GSubBytes;           // 32 KB per buffer
@@ -49,8 +52,8 @@ constexpr int kB2ZCol = 256;
 
 struct B2Bars {
   uint64_t x_full;
-  uint64_t full[kB2Stages];
-  uint64_t empty[kB2Stages];
+  uint64_t full[kB2Slots];
+  uint64_t empty[kB2Slots];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t g_full;
@@ -86,8 +89,8 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary (absent when streamed)
   uint8_t* smem_g = smem_x + (stream_x ? 0 : nk * kB2XChunkBytes);  // 32 KB, single buffer
   uint8_t* smem_g2 = smem_g + kB2GBytes;                 // split mode only: the low-order tile G2
-  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // kB2Stages x 32 KB
-  uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
+  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // kB2Slots x 16 KB
+  uint8_t* smem_coef = smem_ring + kB2Slots * kB2SlotBytes;    // 2 x 4 KB column coefficients
 
   const int ng = (ds + 255) / 256;  // accumulator groups of up to 256 output columns
   const int warp = threadIdx.x >> 5;
@@ -105,7 +108,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
     tma_prefetch_desc(&tm_cols);
     tma_prefetch_desc(&tm_cols_mn);
     mbar_init(&bars.x_full, 1);
-    for (int s = 0; s < kB2Stages; ++s) {
+    for (int s = 0; s < kB2Slots; ++s) {
       mbar_init(&bars.full[s], 1);
       mbar_init(&bars.empty[s], 1);
     }
@@ -142,28 +145,26 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
 #ifdef SCL_LAB_NO_TMA
       int lab_loads = 0;  // lab: only the first round of the ring is really loaded
 #endif
-      // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
+      // one ring slot = one box of up to 16 KB from BOTH CTAs, all credited to the leader's full[s]
       auto acquire = [&](int bytes_per_cta) {
         const int s = ring_s;
         mbar_wait(&bars.empty[s], ring_ph ^ 1);
 #ifdef SCL_LAB_NO_TMA
-        if (lab_loads >= kB2Stages) {
+        if (lab_loads >= kB2Slots) {
           if (leader) mbar_arrive(&bars.full[s]);
         } else
 #endif
         if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
-        if (++ring_s == kB2Stages) {
+        if (++ring_s == kB2Slots) {
           ring_s = 0;
           ring_ph ^= 1;
         }
-        return s;
+        return smem_ring + s * kB2SlotBytes;
       };
 #ifdef SCL_LAB_NO_TMA
-#define SCL_LAB_LOAD(...) do { if (lab_loads < kB2Stages) { __VA_ARGS__; } } while (0)
-#define SCL_LAB_STAGE_DONE() (++lab_loads)
+#define SCL_LAB_LOAD(...) do { if (lab_loads < kB2Slots) { __VA_ARGS__; } ++lab_loads; } while (0)
 #else
 #define SCL_LAB_LOAD(...) do { __VA_ARGS__; } while (0)
-#define SCL_LAB_STAGE_DONE() ((void)0)
 #endif
       auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
@@ -173,23 +174,16 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
         const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
-        if (stream_x) {  // one K chunk per stage: Y chunk in slot 0, X chunk (8 KB) in slot 1
-          for (int kc = 0; kc < nk; ++kc) {
-            const int s = acquire(kB2SlotBytes + kB2XChunkBytes);
-            SCL_LAB_LOAD(
-                tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
-                tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK,
-                                 row0));
-            SCL_LAB_STAGE_DONE();
+        for (int kc = 0; kc < nk; ++kc) {
+          {
+            uint8_t* slot = acquire(kB2SlotBytes);  // Y chunk: this CTA's 128 columns x 64 d
+            uint64_t* bar = &bars.full[(slot - smem_ring) / kB2SlotBytes];
+            SCL_LAB_LOAD(tma_load_2d_pair(slot, &tm_cols, bar, kc * kB2BK, col0));
           }
-        } else {
-          for (int kc = 0; kc < nk; kc += 2) {
-            const int nb = min(2, nk - kc);
-            const int s = acquire(nb * kB2SlotBytes);
-            for (int b = 0; b < nb; ++b)
-              SCL_LAB_LOAD(tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
-                                            (kc + b) * kB2BK, col0));
-            SCL_LAB_STAGE_DONE();
+          if (stream_x) {  // the matching X chunk (8 KB) in a slot of its own
+            uint8_t* slot = acquire(kB2XChunkBytes);
+            uint64_t* bar = &bars.full[(slot - smem_ring) / kB2SlotBytes];
+            SCL_LAB_LOAD(tma_load_2d_pair(slot, &tm_rows, bar, kc * kB2BK, row0));
           }
         }
       };
@@ -198,20 +192,15 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
         for (int p = 0; p < (kSplit ? 3 : 1); ++p) {  // split passes: (G1, Yh), (G1, Yl), (G2, Yh)
           const int p_d0 = (p == 1) ? d : 0;          // Yl sits at columns [d, 2 d) of Y' = (h | l | h)
-          for (int u = 0; u < n_units; u += 2) {
-            const int nb = min(2, n_units - u);
-            const int s = acquire(nb * kB2SlotBytes);
-            for (int b = 0; b < nb; ++b) {
-              const int js = (u + b) / ng, g = (u + b) % ng;
-              const int n_g = min(256, ds - 256 * g);
-              // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
-              const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
-              uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
-              SCL_LAB_LOAD(
-                  tma_load_2d_pair(slot, &tm_cols_mn, &bars.full[s], dbase, col0 + js * 64);
-                  tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.full[s], dbase + 64, col0 + js * 64));
-            }
-            SCL_LAB_STAGE_DONE();
+          for (int u = 0; u < n_units; ++u) {
+            const int js = u / ng, g = u % ng;
+            const int n_g = min(256, ds - 256 * g);
+            // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
+            const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
+            uint8_t* slot = acquire(kB2SlotBytes);
+            uint64_t* bar = &bars.full[(slot - smem_ring) / kB2SlotBytes];
+            SCL_LAB_LOAD(tma_load_2d_pair(slot, &tm_cols_mn, bar, dbase, col0 + js * 64);
+                         tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, bar, dbase + 64, col0 + js * 64));
           }
         }
       };
@@ -232,34 +221,56 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
       tc_fence_after();
       int ring_s = 0;
       uint32_t ring_ph = 0;
-      auto advance = [&]() {
-        if (++ring_s == kB2Stages) {
+      // wait for the next ring slot to be filled; returns its index (the slot is released by release() below)
+      auto next_full = [&]() {
+        const int s = ring_s;
+        mbar_wait_warp(&bars.full[s], ring_ph);
+        if (++ring_s == kB2Slots) {
           ring_s = 0;
           ring_ph ^= 1;
         }
+        return s;
       };
       auto issue_z = [&](int lt) {
         const int buf = lt & 1;
         mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
-        const int kstep = stream_x ? 1 : 2;
-        for (int kc = 0; kc < nk; kc += kstep, advance()) {
-          const int nb = min(kstep, nk - kc);
-          const int s = ring_s;
-          mbar_wait_warp(&bars.full[s], ring_ph);
+        if (stream_x) {  // one K chunk at a time: its Y slot and its X slot
+          for (int kc = 0; kc < nk; ++kc) {
+            const int sy = next_full(), sx = next_full();
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + sx * kB2SlotBytes));
+              const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + sy * kB2SlotBytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_z, (kc | k) != 0 ? 1u : 0u);
+              tc_commit_pair(&bars.empty[sy]);
+              tc_commit_pair(&bars.empty[sx]);
+              if (kc + 1 == nk) tc_commit_pair(&bars.tmem_full[buf]);
+            }
+            __syncwarp();
+          }
+          return;
+        }
+        for (int kc = 0; kc < nk; kc += 2) {  // two K chunks (8 MMAs) per pair of waits
+          const int nb = min(2, nk - kc);
+          int sl[2];
+          sl[0] = next_full();
+          sl[1] = nb > 1 ? next_full() : 0;
           tc_fence_after();
           if (elect_one()) {
-            for (int b = 0; b < nb; ++b) {
-              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(
-                  stream_x ? smem_ring + s * kB2StageBytes + kB2SlotBytes : smem_x + (kc + b) * kB2XChunkBytes));
-              const uint64_t b_desc =
-                  umma_desc_kmajor_sw128(smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes));
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              if (b >= nb) break;
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_x + (kc + b) * kB2XChunkBytes));
+              const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_ring + sl[b] * kB2SlotBytes));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_z, (kc | b | k) != 0 ? 1u : 0u);
+              tc_commit_pair(&bars.empty[sl[b]]);  // the slot goes back as soon as ITS four MMAs have read it
             }
-            tc_commit_pair(&bars.empty[s]);
             if (kc + nb >= nk) tc_commit_pair(&bars.tmem_full[buf]);
           }
           __syncwarp();
@@ -272,25 +283,28 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         constexpr int n_pass = kSplit ? 3 : 1;
         for (int p = 0; p < n_pass; ++p) {
           const uint8_t* g_tile = (kSplit && p == 2) ? smem_g2 : smem_g;
-          for (int u = 0; u < n_units; u += 2, advance()) {
+          for (int u = 0; u < n_units; u += 2) {
             const int nb = min(2, n_units - u);
-            const int s = ring_s;
-            mbar_wait_warp(&bars.full[s], ring_ph);
+            int sl[2];
+            sl[0] = next_full();
+            sl[1] = nb > 1 ? next_full() : 0;
             tc_fence_after();
             if (elect_one()) {
-              for (int b = 0; b < nb; ++b) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                if (b >= nb) break;
                 const int js = (u + b) / ng, g = (u + b) % ng;
                 const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g)) | kUmmaIdescBMnMajor;
                 const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(g_tile + js * kB2GSubBytes));
                 // MN-major Y boxes: 16 contraction rows (columns j) of 128 B = +2048 B per K = 16 step
-                const uint64_t b_desc = umma_desc_mnmajor_sw128(
-                    smem_u32(smem_ring + s * kB2StageBytes + b * kB2SlotBytes), kB2SlotBytes / 2);
+                const uint64_t b_desc =
+                    umma_desc_mnmajor_sw128(smem_u32(smem_ring + sl[b] * kB2SlotBytes), kB2SlotBytes / 2);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 128 * k, idesc_acc,
                                    (lt | p | js | k) != 0 ? 1u : 0u);
+                tc_commit_pair(&bars.empty[sl[b]]);
               }
-              tc_commit_pair(&bars.empty[s]);
               if (p == n_pass - 1 && u + nb >= n_units) tc_commit_pair(&bars.g_empty);
             }
             __syncwarp();
@@ -343,9 +357,17 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
 #ifdef SCL_LAB_NO_EPI
         return z;
 #else
+#ifdef SCL_LAB_NO_LDS
+        const float4 cc = make_float4(60.f + static_cast<float>(j), 1e-3f, 1e-4f, 0.f);
+#else
         const float4 cc = lds_v4(cf + static_cast<uint32_t>(j * 16));  // smem broadcast (same address across the warp)
+#endif
         const float p = ex2_approx(fmaf(z, s2, neg_lr));
+#ifdef SCL_LAB_ONE_EX2
+        const float pc = p * cc.x;
+#else
         const float pc = ex2_approx(fmaf(z, s2, -cc.x));
+#endif
         float g = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
         if (has_diag) g -= (j == diag_col - col0) ? rc.w : 0.f;
         if (ragged) g = (col0 + j < n_cols) ? g : 0.f;
@@ -442,7 +464,7 @@ int bwd_pair_d_slices(int d) {
 
 size_t bwd_pair_smem_bytes(int d, int split) {
   const size_t x_block = (split || d > 512) ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
-  return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
+  return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Slots * kB2SlotBytes + 2 * kB2CoefBytes;
 }
 
 // Column chunks of the backward grid.  Every chunk adds one [m_rows, D] fp32 slab that the kernel writes and

@@ -1,16 +1,9 @@
 """Embedding widths 640 / 1152 / 1280 / 1536 (the remaining open_clip model_configs widths): same kernels as
-768 / 1024 with more D slices in the backward (640 -> 2 x 320 needs a 64-column accumulator group).
-
-EXPERIMENTAL: not yet run on a B200.  The library refuses these widths, and this module is skipped, unless
-SCL_EXPERIMENTAL_SHAPES=1 is set in the environment before the first call."""
-import os
-
+768 / 1024 with more D slices in the backward (640 -> 2 x 320 needs a 64-column accumulator group)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SCL_EXPERIMENTAL_SHAPES") != "1",
-                                 reason="widths beyond 512 / 768 / 1024 not yet run on a B200 (SCL_EXPERIMENTAL_SHAPES=1)")]
+pytestmark = pytest.mark.gpu
 
 LOG2E = 1.4426950408889634
 LN2 = 0.6931471805599453
