@@ -496,8 +496,9 @@ cudaError_t launch_bwd_coeffs(const float4* row_stats, int m_rows, int m_pad, co
 // Reverse lists: the gathered opposite-direction soft-target lists name, per entry e = (row j, slot t >= 1), a column
 // cc; the entries whose column is one of OUR rows (rank*B_l <= cc < (rank+1)*B_l) contribute
 //   dX[cc - rank*B_l, :] -= g*c*(s_eff + k2_owner(j)) * q_jt * Y[j, :].
-// They are bucketed per local row (count -> exclusive scan -> fill; the fill order inside a bucket is arbitrary) and
-// the consumer visits every bucket in ascending e, so the fp32 summation order is fixed from run to run.
+// They are bucketed per local row (count -> bucket allocation -> fill; where a bucket lies and the fill order inside it
+// are arbitrary) and the consumer visits every bucket in ascending e, so the fp32 summation order is fixed from run
+// to run.
 __device__ __forceinline__ bool rev_entry_hits(long long e, int kp1, int b_local, int rank, int col_mode, int cc) {
   const int j = static_cast<int>(e / kp1);
   const int t = static_cast<int>(e - static_cast<long long>(j) * kp1);
@@ -511,29 +512,16 @@ __global__ void __launch_bounds__(256) rev_count_kernel(const int* __restrict__ 
   const int cc = opp_col_all[e];
   if (rev_entry_hits(e, kp1, b_local, rank, col_mode, cc)) atomicAdd(&cnt[cc - rank * b_local], 1);
 }
-// single CTA: off[i] = sum_{i' < i} cnt[i'], off[n] = total; cursor[i] = off[i]
-__global__ void __launch_bounds__(1024) rev_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ off,
-                                                        int* __restrict__ cursor) {
-  __shared__ int sh[1024];
-  const int per = (n + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(n, lo + per);
-  int sum = 0;
-  for (int i = lo; i < hi; ++i) sum += cnt[i];
-  sh[threadIdx.x] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += v;
-    __syncthreads();
-  }
-  int run = sh[threadIdx.x] - sum;
-  for (int i = lo; i < hi; ++i) {
-    off[i] = run;
-    cursor[i] = run;
-    run += cnt[i];
-  }
-  if (threadIdx.x == 1023) off[n] = sh[1023];
+// bucket placement: off[i] = a private range of cnt[i] entries of `list`, handed out by one atomic per non-empty row.
+// WHERE a bucket lies does not matter (the consumer orders every bucket itself), so no prefix scan is needed.
+__global__ void __launch_bounds__(256) rev_alloc_kernel(const int* __restrict__ cnt, int n, int* __restrict__ total,
+                                                        int* __restrict__ off, int* __restrict__ cursor) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cnt[i];
+  const int o = c > 0 ? atomicAdd(total, c) : 0;
+  off[i] = o;
+  cursor[i] = o;
 }
 __global__ void __launch_bounds__(256) rev_fill_kernel(const int* __restrict__ opp_col_all, long long total, int kp1,
                                                        int b_local, int rank, int col_mode, int* __restrict__ cursor,
@@ -545,7 +533,7 @@ __global__ void __launch_bounds__(256) rev_fill_kernel(const int* __restrict__ o
     list[atomicAdd(&cursor[cc - rank * b_local], 1)] = static_cast<int>(e);
 }
 size_t bwd_finish_workspace_bytes(int n_global, int b_local, int kp1) {
-  // cnt[b_local] | off[b_local + 1] | cursor[b_local] | list[n_global * kp1]
+  // cnt[b_local] + total | off[b_local] | cursor[b_local] | list[n_global * kp1]
   return (static_cast<size_t>(3) * b_local + 1 + static_cast<size_t>(n_global) * kp1) * sizeof(int) + 256;
 }
 
@@ -577,7 +565,8 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
                                                          const float* __restrict__ scalars,
                                                          const float* __restrict__ grad_out, float c, float w,
                                                          float mult, int y_ld, int y_lo,
-                                                         const int* __restrict__ rev_off, const int* __restrict__ rev_list,
+                                                         const int* __restrict__ rev_off, const int* __restrict__ rev_cnt,
+                                                         const int* __restrict__ rev_list,
                                                          const float* __restrict__ opp_q_all,
                                                          OutT* __restrict__ dx_out) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -595,7 +584,7 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
   }
   const unsigned own_mask = __ballot_sync(0xffffffffu, my_col >= 0);
   const int r_lo = rev_off != nullptr ? rev_off[row] : 0;
-  const int r_n = rev_off != nullptr ? rev_off[row + 1] - r_lo : 0;
+  const int r_n = rev_off != nullptr ? rev_cnt[row] : 0;
   // the common case (bucket of <= 32 entries): order it once, lane p keeps the p-th smallest entry
   int s_j = 0;
   float s_qc = 0.f;
@@ -674,29 +663,31 @@ cudaError_t launch_bwd_finish(const float* dx_partial, int chunks, int m_pad, in
   const int y_ld = split ? 3 * d : d;  // split: y_all is the (h | l | h) column operand
   const int y_lo = split ? d : -1;
   const int* rev_off = nullptr;
+  const int* rev_cnt = nullptr;
   const int* rev_list = nullptr;
   if (col_mode != 0) {
     if (workspace == nullptr || workspace_bytes < bwd_finish_workspace_bytes(n_global, b_local, kp1))
       return cudaErrorInvalidValue;
-    int* cnt = static_cast<int*>(workspace);
-    int* off = cnt + b_local;
-    int* cursor = off + b_local + 1;
+    int* cnt = static_cast<int*>(workspace);  // cnt[b_local], then the running total
+    int* off = cnt + b_local + 1;
+    int* cursor = off + b_local;
     int* list = cursor + b_local;
     const long long total = static_cast<long long>(n_global) * kp1;
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(b_local) * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(b_local + 1) * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     rev_count_kernel<<<blocks, 256, 0, stream>>>(opp_col_all, total, kp1, b_local, rank, col_mode, cnt);
-    rev_scan_kernel<<<1, 1024, 0, stream>>>(cnt, b_local, off, cursor);
+    rev_alloc_kernel<<<(b_local + 255) / 256, 256, 0, stream>>>(cnt, b_local, cnt + b_local, off, cursor);
     rev_fill_kernel<<<blocks, 256, 0, stream>>>(opp_col_all, total, kp1, b_local, rank, col_mode, cursor, list);
     rev_off = off;
+    rev_cnt = cnt;
     rev_list = list;
   }
   const unsigned grid = (m_rows + 7) / 8;
 #define SCL_GATHER(T)                                                                                                 \
   bwd_gather_kernel<T><<<grid, 256, 0, stream>>>(dx_partial, chunks, m_pad, m_rows, d, yb, pos_col, pos_q, kp1,       \
                                                  b_local, rank, gaps, scalars, grad_out, c, w, mult, y_ld, y_lo,      \
-                                                 rev_off, rev_list, opp_q_all, static_cast<T*>(dx_out))
+                                                 rev_off, rev_cnt, rev_list, opp_q_all, static_cast<T*>(dx_out))
   if (out_dtype == 0) SCL_GATHER(float);
   else if (out_dtype == 1) SCL_GATHER(__nv_bfloat16);
   else SCL_GATHER(__half);

@@ -18,12 +18,10 @@ sys.path.insert(0, str(ROOT))
 
 VARIANTS = {
     "base": [],
-    "slots6": ["-DSCL_B2_SLOTS=6"],
-    "slots5": ["-DSCL_B2_SLOTS=5"],
+    "z4a3": ["-DSCL_B2_ZSLOTS=4", "-DSCL_B2_ASLOTS=3"],
+    "z2a5": ["-DSCL_B2_ZSLOTS=2", "-DSCL_B2_ASLOTS=5"],
+    "z3a3": ["-DSCL_B2_ZSLOTS=3", "-DSCL_B2_ASLOTS=3"],
     "no_epi": ["-DSCL_LAB_NO_EPI"],
-    "one_ex2": ["-DSCL_LAB_ONE_EX2"],
-    "no_lds": ["-DSCL_LAB_NO_LDS"],
-    "one_ex2_no_lds": ["-DSCL_LAB_ONE_EX2", "-DSCL_LAB_NO_LDS"],
     "no_tma": ["-DSCL_LAB_NO_TMA"],
     "no_epi_no_tma": ["-DSCL_LAB_NO_EPI", "-DSCL_LAB_NO_TMA"],
 }
