@@ -387,6 +387,22 @@ def run_ours(args):
     sync_all()
     kernel_events, ops.kernel_events = ops.kernel_events, None
 
+    # ---- optional per-phase timeline of one step (developer aid for the multi-GPU fixed costs): CUDA events at named
+    # points of forward and backward, reported as the GPU time between consecutive marks, max over ranks
+    timeline = None
+    if args.timeline:
+        for _ in range(3):
+            ops.timeline = []
+            step({k: v.detach() for k, v in dev_in.items()})
+            sync_all()
+        tl, ops.timeline = ops.timeline, None
+        names = [f"{tl[i][0]} -> {tl[i + 1][0]}" for i in range(len(tl) - 1)]
+        tt = torch.tensor([tl[i][1].elapsed_time(tl[i + 1][1]) for i in range(len(tl) - 1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        timeline = {n: round(float(v), 4) for n, v in zip(names, tt.tolist())}
+        timeline["sum_ms"] = round(float(tt.sum()), 4)
+
     # ---- end to end: pinned host inputs -> H2D -> module fwd+bwd -> loss D2H, every step.
     # Double-buffered input pipeline: step i+1's H2D copy is enqueued on a copy stream before step i's loss is
     # read back, so PCIe overlaps the kernels; every step's inputs are still copied inside the timed region.
@@ -534,6 +550,7 @@ def run_ours(args):
                      "note": "achieved counts the dX GEMM only (algorithmic); the launch also recomputes the similarity "
                              "tile once (executed = 2x)"},
         "parity": parity,
+        "timeline_ms": timeline,
         "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
                          "sample": cpu_sample_text(cpu)},
     }
@@ -548,6 +565,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)  # 10 warm-up + 50 timed
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--timeline", action="store_true", help="add the per-phase GPU times of one step to the JSON line")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="fp32: the fp32-accurate mode (bf16 hi/lo operand pairs), BASELINE configs[4]'s 'fp32 vs bf16'")
     args = ap.parse_args()

@@ -155,6 +155,16 @@ class CudaOps:
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self.kernel_events = None  # set to {} to record CUDA events around the tensor-core kernels
 
+    def mark(self, name, device):
+        """Developer timeline (bench.py --timeline): a CUDA event on the current stream at a named point of the step;
+        consecutive marks bracket the phases (exchanges, passes, finishes).  No-op unless self.timeline is a list."""
+        tl = getattr(self, "timeline", None)
+        if tl is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        tl.append((name, ev))
+
     def _timed(self, name, device, fn):
         """Run one C-ABI launch, optionally bracketed by CUDA events on its stream (bench.py roofline)."""
         if self.kernel_events is None:
@@ -399,6 +409,7 @@ class CudaOps:
                 for phase, wait in zip((1, 2, 4), waits):
                     if wait is not None:
                         wait()
+                    self.mark(f"fwd:wait{phase}", dev)
                     if phase == 1 and positives is not None:
                         continue
                     if phase == 1 and ids:  # the gathered id vectors exist only now (the wait de-interleaves them)

@@ -15,8 +15,8 @@
 // Y [N, D] (the same bytes as tm_cols, a different box), whose SWIZZLE_128B image is exactly the canonical MN-major
 // UMMA layout (umma_desc_mnmajor_sw128) -- no transposed copy of Y exists anywhere.
 //
-// Barriers (same smem offset in both CTAs): x_full, z_full[s], a_full[s], tmem_empty[b], g_full are waited on by
-// the leader (TMA bytes / remote arrivals from the peer are credited to the leader's copy); z_empty[s], a_empty[s],
+// Barriers (same smem offset in both CTAs): x_full, full[s], tmem_empty[b], g_full are waited on by
+// the leader (TMA bytes / remote arrivals from the peer are credited to the leader's copy); empty[s],
 // tmem_full[b], g_empty, acc_full are multicast by the leader's tcgen05.commit to both CTAs.
 #include "scl_kernels.h"
 #include "scl_ptx.cuh"
@@ -26,36 +26,31 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-constexpr int kB2SlotBytes = 16384;                   // one TMA box pair: [128 cols x 64 d] or 2 x [64 j x 64 d]
+#ifndef SCL_B2_STAGES
+#define SCL_B2_STAGES 3
+#endif
+constexpr int kB2Stages = SCL_B2_STAGES;  // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
+constexpr int kB2SlotBytes = 16384;
+constexpr int kB2StageBytes = 2 * kB2SlotBytes;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
 constexpr int kB2GSubBytes = kB2Rows * 64 * 2;        // 8 KB: [64 rows x 64 cols] bf16
 constexpr int kB2GBytes = 4 * kB2GSubBytes;           // 32 KB per buffer
-constexpr int kB2MaxSlots = 8;                        // per ring
 constexpr int kB2EpiWarps = 16;
-// Warp roles: 0..15 epilogue; 16 TMA producer of the similarity GEMM's operands ("z ring"); 17 its MMA issuer;
-// 18 TMEM allocator, then TMA producer of the gradient GEMM's operands ("a ring"); 19 its MMA issuer.
-// TWO independent issue streams: the similarity GEMM of step lt+1 and the gradient GEMM of step lt depend on different
-// things (a free TMEM buffer vs the G tile of the epilogue) and read different rings, so neither issuer ever sits
-// behind the other one's wait; the tensor pipe takes MMAs from whichever stream has them ready.  (With ONE issuer
-// walking z(lt+1), acc(lt), z(lt+2), ... in program order every late G tile or late TMA box stalled both GEMMs:
-// measured 1.93 ms per launch at N = 32768 against 1.33 ms for the MMA stream alone, tools/bwd_lab.py.)
-// The single-thread roles get the HIGHEST warp ids on purpose: the SM's warp arbiter favours high warp ids, and an
-// MMA issuer shares its scheduler with four busy epilogue warps -- at a low id it was starved of issue slots.
-constexpr int kB2ProdZWarp = kB2EpiWarps;
-constexpr int kB2MmaZWarp = kB2EpiWarps + 1;
-constexpr int kB2ProdAWarp = kB2EpiWarps + 2;  // also allocates / frees TMEM
-constexpr int kB2MmaAWarp = kB2EpiWarps + 3;
-constexpr int kB2Threads = (kB2EpiWarps + 4) * 32;  // 640
+constexpr int kB2Threads = (kB2EpiWarps + 3) * 32;  // 608
+// Warp roles: 0..15 epilogue, 16 TMA producer, 17 MMA issuer, 18 TMEM allocator.  The single-thread roles get
+// the HIGHEST warp ids on purpose: the SM's warp arbiter favours high warp ids, and the MMA issuer shares its
+// scheduler with four busy epilogue warps -- at a low id it was starved of issue slots (measured: ~130 cycles
+// per tcgen05.mma issue against 65 cycles of execution).
+constexpr int kB2ProducerWarp = kB2EpiWarps;
+constexpr int kB2MmaWarp = kB2EpiWarps + 1;
+constexpr int kB2AllocWarp = kB2EpiWarps + 2;
 constexpr int kB2CoefBytes = kB2TileN * 16;           // 4 KB: float4 per column of the step
 constexpr int kB2ZCol = 256;
-constexpr int kB2SmemLimit = 231424;                  // dynamic shared memory asked for (226 KB)
 
 struct B2Bars {
   uint64_t x_full;
-  uint64_t z_full[kB2MaxSlots];
-  uint64_t z_empty[kB2MaxSlots];
-  uint64_t a_full[kB2MaxSlots];
-  uint64_t a_empty[kB2MaxSlots];
+  uint64_t full[kB2Stages];
+  uint64_t empty[kB2Stages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t g_full;
@@ -65,38 +60,6 @@ struct B2Bars {
   uint64_t coef_empty[2];
   uint32_t tmem_base;
 };
-
-// Shared-memory plan: resident X block (one D slice, bf16 mode) | G (| G2) | z ring | a ring | coefficients.
-// z slots hold one K chunk of this CTA's Y half (16 KB) plus, when X is streamed, the matching X chunk (8 KB).
-struct B2Layout {
-  int x_bytes, g_bytes, z_slot_bytes, z_slots, a_slots;
-  size_t total;
-};
-B2Layout bwd_pair_layout(int d, int split) {
-  B2Layout l;
-  const bool stream_x = split || d > 512;
-  l.x_bytes = stream_x ? 0 : (d / kB2BK) * kB2XChunkBytes;
-  l.g_bytes = (split ? 2 : 1) * kB2GBytes;
-  l.z_slot_bytes = kB2SlotBytes + (stream_x ? kB2XChunkBytes : 0);
-  const int avail = kB2SmemLimit - 1024 - l.x_bytes - l.g_bytes - 2 * kB2CoefBytes;
-#ifdef SCL_B2_ZSLOTS
-  l.z_slots = SCL_B2_ZSLOTS;
-#else
-  l.z_slots = 3;
-#endif
-  l.a_slots = (avail - l.z_slots * l.z_slot_bytes) / kB2SlotBytes;
-  if (l.a_slots > kB2MaxSlots) {  // room to spare (narrow D): grow the z ring too
-    l.a_slots = kB2MaxSlots;
-    l.z_slots = (avail - l.a_slots * kB2SlotBytes) / l.z_slot_bytes;
-    if (l.z_slots > kB2MaxSlots) l.z_slots = kB2MaxSlots;
-  }
-#ifdef SCL_B2_ASLOTS
-  l.a_slots = SCL_B2_ASLOTS;
-#endif
-  l.total = 1024 + static_cast<size_t>(l.x_bytes) + l.g_bytes + static_cast<size_t>(l.z_slots) * l.z_slot_bytes +
-            static_cast<size_t>(l.a_slots) * kB2SlotBytes + 2 * kB2CoefBytes;
-  return l;
-}
 
 // kSplit = 1 is the fp32-accurate ("bf16x2") mode: every operand is a bf16 hi + lo pair.  The similarity is
 // contracted over the K-concatenated rows X' = (h|h|l), Y' = (h|l|h) of width 3 d (x.y ~= xh.yh + xh.yl + xl.yh,
@@ -108,26 +71,23 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
                      const __grid_constant__ CUtensorMap tm_cols,     // Y [N, kd]  box {64, 128}
                      const __grid_constant__ CUtensorMap tm_cols_mn,  // Y [N, kd]  box {64, 64}
                      int m_rows, int n_cols, int d, int d_slices, int n_tiles, int tiles_per_chunk, int m_pad,
-                     int diag0, int z_slots, int a_slots, const float* __restrict__ scale_log2_ptr,
-                     const float4* __restrict__ row_coef, const float4* __restrict__ col_coef,
-                     float* __restrict__ dx_partial) {
+                     int diag0, const float* __restrict__ scale_log2_ptr, const float4* __restrict__ row_coef,
+                     const float4* __restrict__ col_coef, float* __restrict__ dx_partial) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ B2Bars bars;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = (kSplit ? 3 * d : d) / kB2BK;  // K chunks of the similarity contraction
   // D <= 512: one D slice, X block resident.  D > 512 (TMEM cannot hold dX[64 x D]): blockIdx.z selects a
   // slice of ds = D / d_slices output columns; z is still contracted over all of D, with the X chunks
-  // streamed through the z ring next to the Y chunks.
+  // streamed through the ring next to the Y chunks.
   const bool stream_x = kSplit != 0 || d_slices > 1;
-  const int z_slot_bytes = kB2SlotBytes + (stream_x ? kB2XChunkBytes : 0);
   const int ds = d / d_slices;
   const int d0 = static_cast<int>(blockIdx.z) * ds;
   uint8_t* smem_x = smem;                                // nk x 8 KB, stationary (absent when streamed)
   uint8_t* smem_g = smem_x + (stream_x ? 0 : nk * kB2XChunkBytes);  // 32 KB, single buffer
   uint8_t* smem_g2 = smem_g + kB2GBytes;                 // split mode only: the low-order tile G2
-  uint8_t* ring_z = smem_g + (kSplit ? 2 : 1) * kB2GBytes;
-  uint8_t* ring_a = ring_z + z_slots * z_slot_bytes;
-  uint8_t* smem_coef = ring_a + a_slots * kB2SlotBytes;  // 2 x 4 KB column coefficients
+  uint8_t* smem_ring = smem_g + (kSplit ? 2 : 1) * kB2GBytes;  // kB2Stages x 32 KB
+  uint8_t* smem_coef = smem_ring + kB2Stages * kB2StageBytes;  // 2 x 4 KB column coefficients
 
   const int ng = (ds + 255) / 256;  // accumulator groups of up to 256 output columns
   const int warp = threadIdx.x >> 5;
@@ -140,16 +100,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
   const int t_end = min(t_begin + tiles_per_chunk, n_tiles);
   const int n_my = t_end - t_begin;
 
-  if (warp == kB2ProdZWarp && lane == 0) {
+  if (warp == kB2ProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_rows);
     tma_prefetch_desc(&tm_cols);
     tma_prefetch_desc(&tm_cols_mn);
     mbar_init(&bars.x_full, 1);
-    for (int s = 0; s < kB2MaxSlots; ++s) {
-      mbar_init(&bars.z_full[s], 1);
-      mbar_init(&bars.z_empty[s], 1);
-      mbar_init(&bars.a_full[s], 1);
-      mbar_init(&bars.a_empty[s], 1);
+    for (int s = 0; s < kB2Stages; ++s) {
+      mbar_init(&bars.full[s], 1);
+      mbar_init(&bars.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars.tmem_full[b], 1);
@@ -162,7 +120,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
     mbar_init(&bars.acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == kB2ProdAWarp) {
+  if (warp == kB2AllocWarp) {
     tmem_alloc_pair(&bars.tmem_base, 512);
     tmem_relinquish_pair();
   }
@@ -171,29 +129,43 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
-#ifdef SCL_LAB_NO_TMA
-#define SCL_LAB_LOAD(...) do { if (lab_loads < lab_limit) { __VA_ARGS__; } ++lab_loads; } while (0)
-#define SCL_LAB_EXPECT(bar, bytes) do { if (lab_loads >= lab_limit) { if (leader) mbar_arrive(bar); } else if (leader) mbar_arrive_expect_tx(bar, bytes); } while (0)
-#else
-#define SCL_LAB_LOAD(...) do { __VA_ARGS__; } while (0)
-#define SCL_LAB_EXPECT(bar, bytes) do { if (leader) mbar_arrive_expect_tx(bar, bytes); } while (0)
-#endif
-
-  if (warp == kB2ProdZWarp) {
-    // ------------------------------------------------------------ TMA producer of the similarity GEMM (one thread)
+  if (warp == kB2ProducerWarp) {
+    // ------------------------------------------------------------ TMA producer (one thread per CTA)
     if (lane == 0) {
       if (!stream_x) {
         if (leader) mbar_arrive_expect_tx(&bars.x_full, static_cast<uint32_t>(2 * nk * kB2XChunkBytes));
         for (int kc = 0; kc < nk; ++kc)
           tma_load_2d_pair(smem_x + kc * kB2XChunkBytes, &tm_rows, &bars.x_full, kc * kB2BK, row0);
       }
+      int ring_s = 0;
+      uint32_t ring_ph = 0;
 #ifdef SCL_LAB_NO_TMA
       int lab_loads = 0;  // lab: only the first round of the ring is really loaded
-      const int lab_limit = z_slots;
 #endif
-      int s = 0;
-      uint32_t ph = 0;
-      for (int lt = 0; lt < n_my; ++lt) {
+      // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
+      auto acquire = [&](int bytes_per_cta) {
+        const int s = ring_s;
+        mbar_wait(&bars.empty[s], ring_ph ^ 1);
+#ifdef SCL_LAB_NO_TMA
+        if (lab_loads >= kB2Stages) {
+          if (leader) mbar_arrive(&bars.full[s]);
+        } else
+#endif
+        if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
+        if (++ring_s == kB2Stages) {
+          ring_s = 0;
+          ring_ph ^= 1;
+        }
+        return s;
+      };
+#ifdef SCL_LAB_NO_TMA
+#define SCL_LAB_LOAD(...) do { if (lab_loads < kB2Stages) { __VA_ARGS__; } } while (0)
+#define SCL_LAB_STAGE_DONE() (++lab_loads)
+#else
+#define SCL_LAB_LOAD(...) do { __VA_ARGS__; } while (0)
+#define SCL_LAB_STAGE_DONE() ((void)0)
+#endif
+      auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
         const int cb = lt & 1;
         mbar_wait(&bars.coef_empty[cb], ((lt >> 1) & 1) ^ 1);
@@ -201,124 +173,159 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         bulk_load_1d(smem_coef + cb * kB2CoefBytes, col_coef + static_cast<size_t>(t_begin + lt) * kB2TileN,
                      kB2CoefBytes, &bars.coef_full[cb]);
         const int col0 = (t_begin + lt) * kB2TileN + static_cast<int>(cta) * 128;
-        for (int kc = 0; kc < nk; ++kc) {
-          // one slot = this CTA's [128 cols x 64 d] Y chunk (+ the X chunk) from BOTH CTAs, credited to the leader
-          mbar_wait(&bars.z_empty[s], ph ^ 1);
-          SCL_LAB_EXPECT(&bars.z_full[s], static_cast<uint32_t>(2 * z_slot_bytes));
-          uint8_t* slot = ring_z + s * z_slot_bytes;
-          SCL_LAB_LOAD(tma_load_2d_pair(slot, &tm_cols, &bars.z_full[s], kc * kB2BK, col0);
-                       if (stream_x) tma_load_2d_pair(slot + kB2SlotBytes, &tm_rows, &bars.z_full[s], kc * kB2BK, row0));
-          if (++s == z_slots) {
-            s = 0;
-            ph ^= 1;
+        if (stream_x) {  // one K chunk per stage: Y chunk in slot 0, X chunk (8 KB) in slot 1
+          for (int kc = 0; kc < nk; ++kc) {
+            const int s = acquire(kB2SlotBytes + kB2XChunkBytes);
+            SCL_LAB_LOAD(
+                tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+                tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK,
+                                 row0));
+            SCL_LAB_STAGE_DONE();
+          }
+        } else {
+          for (int kc = 0; kc < nk; kc += 2) {
+            const int nb = min(2, nk - kc);
+            const int s = acquire(nb * kB2SlotBytes);
+            for (int b = 0; b < nb; ++b)
+              SCL_LAB_LOAD(tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
+                                            (kc + b) * kB2BK, col0));
+            SCL_LAB_STAGE_DONE();
           }
         }
-      }
-    }
-  } else if (warp == kB2ProdAWarp) {
-    // ------------------------------------------------------------ TMA producer of the gradient GEMM (one thread)
-    if (lane == 0) {
-#ifdef SCL_LAB_NO_TMA
-      int lab_loads = 0;
-      const int lab_limit = a_slots;
-#endif
-      int s = 0;
-      uint32_t ph = 0;
-      const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
-      for (int lt = 0; lt < n_my; ++lt) {
+      };
+      auto push_y = [&](int lt) {
         const int col0 = (t_begin + lt) * kB2TileN;
+        const int n_units = 4 * ng;  // unit u = (64-column sub-tile js = u / ng, accumulator group g = u % ng)
         for (int p = 0; p < (kSplit ? 3 : 1); ++p) {  // split passes: (G1, Yh), (G1, Yl), (G2, Yh)
           const int p_d0 = (p == 1) ? d : 0;          // Yl sits at columns [d, 2 d) of Y' = (h | l | h)
-          for (int u = 0; u < n_units; ++u) {
-            const int js = u / ng, g = u % ng;
-            const int n_g = min(256, ds - 256 * g);
-            // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
-            const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
-            mbar_wait(&bars.a_empty[s], ph ^ 1);
-            SCL_LAB_EXPECT(&bars.a_full[s], static_cast<uint32_t>(2 * kB2SlotBytes));
-            uint8_t* slot = ring_a + s * kB2SlotBytes;
-            SCL_LAB_LOAD(tma_load_2d_pair(slot, &tm_cols_mn, &bars.a_full[s], dbase, col0 + js * 64);
-                         tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.a_full[s], dbase + 64,
-                                          col0 + js * 64));
-            if (++s == a_slots) {
-              s = 0;
-              ph ^= 1;
+          for (int u = 0; u < n_units; u += 2) {
+            const int nb = min(2, n_units - u);
+            const int s = acquire(nb * kB2SlotBytes);
+            for (int b = 0; b < nb; ++b) {
+              const int js = (u + b) / ng, g = (u + b) % ng;
+              const int n_g = min(256, ds - 256 * g);
+              // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
+              const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
+              uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
+              SCL_LAB_LOAD(
+                  tma_load_2d_pair(slot, &tm_cols_mn, &bars.full[s], dbase, col0 + js * 64);
+                  tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.full[s], dbase + 64, col0 + js * 64));
             }
+            SCL_LAB_STAGE_DONE();
           }
         }
+      };
+      push_z(0);
+      for (int lt = 0; lt < n_my; ++lt) {
+        if (lt + 1 < n_my) push_z(lt + 1);
+        push_y(lt);
       }
     }
-  } else if (warp == kB2MmaZWarp) {
-    // ------------------------------------------------------------ MMA issuer of the similarity GEMM (leader CTA)
-    // Whole warp converged, one elected lane issues (see scl_fwd2.cu); one ring slot = four MMAs per wait.
+  } else if (warp == kB2MmaWarp) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    // Whole warp converged, one elected lane issues (see scl_fwd2.cu).  Each barrier wait releases up to
+    // 8 MMAs (two 16 KB boxes): a wait + commit round trip costs the issuing thread ~250 cycles, which at 4
+    // MMAs of 65 cycles per wait left the tensor pipe under-fed.
     if (leader) {
       constexpr uint32_t idesc_z = umma_idesc_bf16(128, kB2TileN);
       if (!stream_x) mbar_wait_warp(&bars.x_full, 0);
       tc_fence_after();
-      int s = 0;
-      uint32_t ph = 0;
-      for (int lt = 0; lt < n_my; ++lt) {
+      // Everything an MMA batch needs besides the data is computed BEFORE the wait for that data: the shared-memory
+      // descriptors are base + offset in the 16-byte address field (all operands live below 256 KB), pinned in
+      // registers by an empty asm so that the compiler cannot sink the arithmetic behind the barrier.  With the
+      // arithmetic (~35 dependent uniform-datapath instructions) between the wait and the first UTCHMMA the tensor
+      // pipe drained for ~150 cycles per batch (measured: 77 % pipe activity with all operands resident).
+      const uint64_t x_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_x));
+      const uint64_t ring_k0 = umma_desc_kmajor_sw128(smem_u32(smem_ring));
+      const uint64_t ring_mn0 = umma_desc_mnmajor_sw128(smem_u32(smem_ring), kB2SlotBytes / 2);
+      const uint64_t g_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_g));
+      constexpr uint64_t kSlotUnits = kB2SlotBytes >> 4, kStageUnits = kB2StageBytes >> 4;
+      const int ng_shift = ng - 1;  // ng is 1 or 2
+      const uint32_t idesc_acc0 = umma_idesc_bf16(128, min(256, ds)) | kUmmaIdescBMnMajor;
+      const uint32_t idesc_acc1 = umma_idesc_bf16(128, max(16, min(256, ds - 256))) | kUmmaIdescBMnMajor;
+      int ring_s = 0;
+      uint32_t ring_ph = 0;
+      auto advance = [&]() {
+        if (++ring_s == kB2Stages) {
+          ring_s = 0;
+          ring_ph ^= 1;
+        }
+      };
+      auto issue_z = [&](int lt) {
         const int buf = lt & 1;
         mbar_wait_warp(&bars.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kB2ZCol + buf * 128;
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait_warp(&bars.z_full[s], ph);
+        const int kstep = stream_x ? 1 : 2;
+        for (int kc = 0; kc < nk; kc += kstep, advance()) {
+          const int nb = min(kstep, nk - kc);
+          const int s = ring_s;
+          uint64_t b_desc = ring_k0 + static_cast<uint64_t>(s) * kStageUnits;
+          uint64_t a_desc = stream_x ? b_desc + kSlotUnits : x_desc0 + static_cast<uint64_t>(kc) * (kB2XChunkBytes >> 4);
+          uint32_t bar_full = smem_u32(&bars.full[s]), bar_empty = smem_u32(&bars.empty[s]);
+          asm volatile("" : "+l"(a_desc), "+l"(b_desc), "+r"(bar_full), "+r"(bar_empty));
+          mbar_wait_warp_u32(bar_full, ring_ph);
           tc_fence_after();
           if (elect_one()) {
-            const uint8_t* slot = ring_z + s * z_slot_bytes;
-            const uint64_t a_desc =
-                umma_desc_kmajor_sw128(smem_u32(stream_x ? slot + kB2SlotBytes : smem_x + kc * kB2XChunkBytes));
-            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(slot));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_z, (kc | k) != 0 ? 1u : 0u);
-            tc_commit_pair(&bars.z_empty[s]);
-            if (kc + 1 == nk) tc_commit_pair(&bars.tmem_full[buf]);
-          }
-          __syncwarp();
-          if (++s == z_slots) {
-            s = 0;
-            ph ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == kB2MmaAWarp) {
-    // ------------------------------------------------------------ MMA issuer of the gradient GEMM (leader CTA)
-    if (leader) {
-      int s = 0;
-      uint32_t ph = 0;
-      const int n_units = 4 * ng;
-      constexpr int n_pass = kSplit ? 3 : 1;
-      for (int lt = 0; lt < n_my; ++lt) {
-        mbar_wait_warp(&bars.g_full, lt & 1);
-        tc_fence_after();
-        for (int p = 0; p < n_pass; ++p) {
-          const uint8_t* g_tile = (kSplit && p == 2) ? smem_g2 : smem_g;
-          for (int u = 0; u < n_units; ++u) {
-            mbar_wait_warp(&bars.a_full[s], ph);
-            tc_fence_after();
-            if (elect_one()) {
-              const int js = u / ng, g = u % ng;
-              const uint32_t idesc_acc = umma_idesc_bf16(128, min(256, ds - 256 * g)) | kUmmaIdescBMnMajor;
-              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(g_tile + js * kB2GSubBytes));
-              // MN-major Y boxes: 16 contraction rows (columns j) of 128 B = +2048 B per K = 16 step
-              const uint64_t b_desc = umma_desc_mnmajor_sw128(smem_u32(ring_a + s * kB2SlotBytes), kB2SlotBytes / 2);
+            if (nb > 1) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                tc_mma_bf16_pair(tmem_base + g * 128, a_desc + 2 * k, b_desc + 128 * k, idesc_acc,
-                                 (lt | p | js | k) != 0 ? 1u : 0u);
-              tc_commit_pair(&bars.a_empty[s]);
-              if (p == n_pass - 1 && u + 1 == n_units) tc_commit_pair(&bars.g_empty);
+                tc_mma_bf16_pair(d_tmem, a_desc + (kB2XChunkBytes >> 4) + 2 * k, b_desc + kSlotUnits + 2 * k, idesc_z, 1u);
+            }
+            tc_commit_pair_u32(bar_empty);
+            if (kc + nb >= nk) tc_commit_pair(&bars.tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+      };
+      auto issue_acc = [&](int lt) {
+        mbar_wait_warp(&bars.g_full, lt & 1);
+        tc_fence_after();
+        const int n_units = 4 * ng;
+        constexpr int n_pass = kSplit ? 3 : 1;
+        for (int p = 0; p < n_pass; ++p) {
+          const uint64_t g_base = (kSplit && p == 2) ? g_desc0 + (kB2GBytes >> 4) : g_desc0;
+          for (int u = 0; u < n_units; u += 2, advance()) {
+            const int nb = min(2, n_units - u);
+            const int s = ring_s;
+            uint64_t b_desc = ring_mn0 + static_cast<uint64_t>(s) * kStageUnits;
+            // unit u -> (64-column G sub-tile js, accumulator group g); u is even, so unit u + 1 is (js, 1) when
+            // there are two groups and (js + 1, 0) when there is one
+            const int js0 = u >> ng_shift;
+            uint64_t a_desc0 = g_base + static_cast<uint64_t>(js0) * (kB2GSubBytes >> 4);
+            uint64_t a_desc1 = g_base + static_cast<uint64_t>((u + 1) >> ng_shift) * (kB2GSubBytes >> 4);
+            uint32_t bar_full = smem_u32(&bars.full[s]), bar_empty = smem_u32(&bars.empty[s]);
+            asm volatile("" : "+l"(a_desc0), "+l"(a_desc1), "+l"(b_desc), "+r"(bar_full), "+r"(bar_empty));
+            mbar_wait_warp_u32(bar_full, ring_ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t acc_first = (lt | p | js0) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16_pair(tmem_base, a_desc0 + 2 * k, b_desc + 128 * k, idesc_acc0, (acc_first | k) != 0 ? 1u : 0u);
+              if (nb > 1) {
+                // second unit: group 1 of the same sub-tile (fresh accumulator at js == 0) or group 0 of the next one
+                const uint32_t t1 = tmem_base + (ng > 1 ? 128u : 0u);
+                const uint32_t id1 = ng > 1 ? idesc_acc1 : idesc_acc0;
+                const uint32_t acc1 = ng > 1 ? acc_first : 1u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_bf16_pair(t1, a_desc1 + 2 * k, b_desc + kSlotUnits + 128 * k, id1, (acc1 | k) != 0 ? 1u : 0u);
+              }
+              tc_commit_pair_u32(bar_empty);
+              if (p == n_pass - 1 && u + nb >= n_units) tc_commit_pair(&bars.g_empty);
             }
             __syncwarp();
-            if (++s == a_slots) {
-              s = 0;
-              ph ^= 1;
-            }
           }
         }
+      };
+      issue_z(0);
+      for (int lt = 0; lt < n_my; ++lt) {
+        if (lt + 1 < n_my) issue_z(lt + 1);
+        issue_acc(lt);
       }
       if (elect_one()) tc_commit_pair(&bars.acc_full);
       __syncwarp();
@@ -418,10 +425,14 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         }
         // single G buffer: the second GEMM of the previous step must have consumed it
         mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1);
+#ifndef SCL_LAB_NO_STS
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
           sts_v4(g_u32 + g_off + static_cast<uint32_t>(((c16 + ch) ^ (r_loc & 7)) * 16), packed[ch * 4 + 0],
                  packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+#else
+        if (packed[0] == 0x12345678u && packed[7] == 0x9abcdef0u) sts_v4(g_u32 + g_off, packed[0], packed[1], packed[2], packed[3]);
+#endif
       }
       fence_proxy_async();
       __syncwarp();
@@ -450,7 +461,7 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == kB2ProdAWarp) {
+  if (warp == kB2AllocWarp) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
@@ -466,7 +477,10 @@ int bwd_pair_d_slices(int d) {
   return 0;
 }
 
-size_t bwd_pair_smem_bytes(int d, int split) { return bwd_pair_layout(d, split).total; }
+size_t bwd_pair_smem_bytes(int d, int split) {
+  const size_t x_block = (split || d > 512) ? 0 : static_cast<size_t>(d / kB2BK) * kB2XChunkBytes;
+  return 1024 + x_block + (split ? 2 : 1) * kB2GBytes + kB2Stages * kB2StageBytes + 2 * kB2CoefBytes;
+}
 
 // Column chunks of the backward grid.  Every chunk adds one [m_rows, D] fp32 slab that the kernel writes and
 // bwd_gather reads back (~4 us at 4096 x 512 = 0.9 of a tile-step): charged per chunk, scaled by the slab size.
@@ -483,19 +497,18 @@ static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUte
                                           int tiles_per_chunk, int m_pad, int diag0, const float* scale_log2,
                                           const float4* row_coef, const float4* col_coef, float* dx_partial,
                                           cudaStream_t stream) {
-  const B2Layout lay = bwd_pair_layout(d, kSplit);
-  if (lay.z_slots < 2 || lay.a_slots < 2 || lay.total > static_cast<size_t>(kB2SmemLimit)) return cudaErrorInvalidValue;
+  const size_t smem = bwd_pair_smem_bytes(d, kSplit);
   // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state)
   cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kB2SmemLimit);
+                                         231424);
   if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 127) / 128;
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;
   const int d_slices = bwd_pair_d_slices(d);
   dim3 grid(2 * pairs, chunks, d_slices);
-  bwd_rows_pair_kernel<kSplit><<<grid, kB2Threads, lay.total, stream>>>(
-      tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d, d_slices, n_tiles, tiles_per_chunk, m_pad, diag0, lay.z_slots,
-      lay.a_slots, scale_log2, row_coef, col_coef, dx_partial);
+  bwd_rows_pair_kernel<kSplit><<<grid, kB2Threads, smem, stream>>>(tm_rows, tm_cols, tm_cols_mn, m_rows, n_cols, d,
+                                                                   d_slices, n_tiles, tiles_per_chunk, m_pad, diag0,
+                                                                   scale_log2, row_coef, col_coef, dx_partial);
   return cudaGetLastError();
 }
 

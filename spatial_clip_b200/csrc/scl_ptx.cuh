@@ -66,6 +66,21 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   mbar_wait(bar, parity);
   __syncwarp();
 }
+// the same with the barrier's shared-window address already in a register (computed before the wait is needed)
+__device__ __forceinline__ void mbar_wait_warp_u32(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0, ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > SCL_SPIN_LIMIT) __trap();
+  } while (!ok);
+  __syncwarp();
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
@@ -183,6 +198,12 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_u32(uint32_t bar_addr) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar_addr), "h"(static_cast<uint16_t>(3))
       : "memory");
 }
 // D[tmem, both CTAs] (+)= A * B^T across a CTA pair: each CTA supplies its half of A's rows and of B's rows

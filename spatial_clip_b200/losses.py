@@ -133,8 +133,11 @@ class _ContrastiveLossFn(torch.autograd.Function):
         # ---- cap + bf16 copies of the local rows (the operands of gather_features, loss.py:21-65): one launch.
         # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
         # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
+        mark = getattr(ops, "mark", lambda name, device: None)
+        mark("fwd:start", dev)
         img_l, txt_l, img_c, txt_c, scalars = ops.prepare(
             image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap, split=cfg.split)
+        mark("fwd:prepared", dev)
 
         # ---- exchanges (W > 1), all issued up front without waiting, in the order their consumers run: tile ids (one
         # packed [2, B_l] record: both id vectors, losses.py:63-68) -> soft targets; gene features -> image-rows pass;
@@ -185,6 +188,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
             img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
             finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}),
             **({"positives": positives} if positives is not None else {}))
+        mark("fwd:passes", dev)
         if ranks is None:
             ranks = torch.empty((0,), dtype=torch.int32, device=dev)
         if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
@@ -214,6 +218,8 @@ class _ContrastiveLossFn(torch.autograd.Function):
         b_local, d = img_l.shape[0], ctx.d
         n = world * b_local
         go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        mark = getattr(ops, "mark", lambda name, device: None)
+        mark("bwd:start", img_l.device)
         mode = _col_mode(cfg)
         global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
 
@@ -240,6 +246,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
             col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti
             gaps = out4[1:2].contiguous()
 
+        mark("bwd:exchanged", img_l.device)
         mult = float(world) if (global_clip and cfg.gather_with_grad) else 1.0
         w = cfg.temp_reg_weight
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -248,10 +255,12 @@ class _ContrastiveLossFn(torch.autograd.Function):
             d_img = ops.backward_dir(img_l, txt_all, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
                                      b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0], q_ti,
                                      split=cfg.split)
+            mark("bwd:d_image", img_l.device)
         if need_t:
             d_txt = ops.backward_dir(txt_l, img_all, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
                                      b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1], q_it,
                                      split=cfg.split)
+            mark("bwd:d_text", img_l.device)
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(device=ctx.scale_device, dtype=ctx.in_dtypes[2]).reshape(ctx.scale_shape)

@@ -18,12 +18,12 @@ sys.path.insert(0, str(ROOT))
 
 VARIANTS = {
     "base": [],
-    "z4a3": ["-DSCL_B2_ZSLOTS=4", "-DSCL_B2_ASLOTS=3"],
-    "z2a5": ["-DSCL_B2_ZSLOTS=2", "-DSCL_B2_ASLOTS=5"],
-    "z3a3": ["-DSCL_B2_ZSLOTS=3", "-DSCL_B2_ASLOTS=3"],
+    "no_lds": ["-DSCL_LAB_NO_LDS"],
+    "no_sts": ["-DSCL_LAB_NO_STS"],
+    "one_ex2": ["-DSCL_LAB_ONE_EX2"],
+    "no_lds_no_sts": ["-DSCL_LAB_NO_LDS", "-DSCL_LAB_NO_STS"],
+    "no_lds_no_sts_one_ex2": ["-DSCL_LAB_NO_LDS", "-DSCL_LAB_NO_STS", "-DSCL_LAB_ONE_EX2"],
     "no_epi": ["-DSCL_LAB_NO_EPI"],
-    "no_tma": ["-DSCL_LAB_NO_TMA"],
-    "no_epi_no_tma": ["-DSCL_LAB_NO_EPI", "-DSCL_LAB_NO_TMA"],
 }
 
 
@@ -87,7 +87,7 @@ if __name__ == "__main__":
         build()
     elif sys.argv[1] == "run":
         for name in VARIANTS:
-            for shape in ((32768, 32768), (4096, 32768)):
+            for shape in ((32768, 32768),):
                 r = subprocess.run([sys.executable, __file__, "one", name, str(shape[0]), str(shape[1])],
                                    capture_output=True, text=True, timeout=300)
                 print(r.stdout.strip() or r.stderr[-800:], flush=True)
