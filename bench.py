@@ -365,6 +365,19 @@ def run_ours(args):
     ms, med = float(t[0].item()), float(t[1].item())
     loss_val = float(loss.detach())
 
+    # ---- host cost of a step: wall time to ENQUEUE ten steps on an idle device (no synchronisation inside); when this
+    # exceeds the device time per step the job is host-bound (the case to watch at 8 ranks, ~1 ms of kernels per step)
+    sync_all()
+    h0 = time.perf_counter()
+    for _ in range(10):
+        step({k: v.detach() for k, v in dev_in.items()})
+    host_ms = (time.perf_counter() - h0) * 1e3 / 10
+    sync_all()
+    th = torch.tensor([host_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    host_ms = float(th.item())
+
     # ---- parity inputs: every rank's loss, d logit_scale and a fixed sample of its gradient rows (last timed step)
     from oracle.blockwise_oracle import sample_rows_for
 
@@ -476,6 +489,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
 
+    losses.release_cuda_graphs()  # captured NCCL kernels must go before the process group does
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -527,6 +541,7 @@ def run_ours(args):
         "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "steps": e2e_steps, "pipeline": e2e_note},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel", "achieved": achieved, "peak": pk["burst"],
                      "unit": "TFLOP/s", "frac": achieved / pk["burst"], "traffic": traffic,

@@ -148,6 +148,7 @@ class CudaOps:
     tensors' device and returns without synchronising."""
 
     name = "cuda"
+    graph_capable = True  # every method only enqueues work on the current stream: safe under CUDA-graph capture
 
     def __init__(self):
         self.lib = load_library()

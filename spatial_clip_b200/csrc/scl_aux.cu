@@ -517,11 +517,22 @@ __global__ void __launch_bounds__(256) rev_count_kernel(const int* __restrict__ 
 __global__ void __launch_bounds__(256) rev_alloc_kernel(const int* __restrict__ cnt, int n, int* __restrict__ total,
                                                         int* __restrict__ off, int* __restrict__ cursor) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int c = cnt[i];
-  const int o = c > 0 ? atomicAdd(total, c) : 0;
-  off[i] = o;
-  cursor[i] = o;
+  const int lane = threadIdx.x & 31;
+  const int c = i < n ? cnt[i] : 0;
+  // one atomic per warp: inclusive prefix of the lanes' counts, the last lane reserves the warp's range
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int base = 0;
+  if (lane == 31 && incl > 0) base = atomicAdd(total, incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (i < n) {
+    off[i] = base + incl - c;
+    cursor[i] = base + incl - c;
+  }
 }
 __global__ void __launch_bounds__(256) rev_fill_kernel(const int* __restrict__ opp_col_all, long long total, int kp1,
                                                        int b_local, int rank, int col_mode, int* __restrict__ cursor,
@@ -557,7 +568,25 @@ __device__ __forceinline__ void fma_row4(float4& acc, float qc, const __nv_bfloa
 // written as fp32 (OutT = float) or cast on the way out.  y_ld: row pitch of y_all in elements; y_lo >= 0
 // (fp32-accurate mode): offset of the low-order bf16 part of every row.
 template <typename OutT>
-__global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
+__device__ __forceinline__ void store4(OutT* dst, const float4& v) {
+  if constexpr (std::is_same<OutT, float>::value) {
+    *reinterpret_cast<float4*>(dst) = v;
+  } else if constexpr (std::is_same<OutT, __nv_bfloat16>::value) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst) = pk;
+  } else {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst) = pk;
+  }
+}
+template <typename OutT>
+__global__ void __launch_bounds__(256, 4) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
                                                          int m_rows, int d, const __nv_bfloat16* __restrict__ y_all,
                                                          const int* __restrict__ pos_col,
                                                          const float* __restrict__ pos_q, int kp1, int b_local, int rank,
@@ -572,25 +601,25 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= m_rows) return;
+  // ---- everything the lists need is requested first (independent loads), the long row streams follow
+  int my_col = -1;
+  float my_q = 0.f;
+  if (lane >= 1 && lane < kp1) {  // own list: lane t holds slot t (slot 0 is handled inside the tensor-core kernel)
+    my_col = pos_col[static_cast<size_t>(row) * kp1 + lane];
+    my_q = pos_q[static_cast<size_t>(row) * kp1 + lane];
+  }
+  const int r_lo = rev_off != nullptr ? rev_off[row] : 0;
+  const int r_n = rev_off != nullptr ? rev_cnt[row] : 0;
   const float base = grad_out[0] * mult * c;
   const float s_eff = scalars[0];
   const float coef = base * (s_eff + 2.f * w * gaps[rank]);
-  // own list: lane t holds slot t
-  int my_col = -1;
-  float my_qc = 0.f;
-  if (lane >= 1 && lane < kp1) {
-    my_col = pos_col[static_cast<size_t>(row) * kp1 + lane];
-    my_qc = -coef * pos_q[static_cast<size_t>(row) * kp1 + lane];
-  }
+  const float my_qc = -coef * my_q;
   const unsigned own_mask = __ballot_sync(0xffffffffu, my_col >= 0);
-  const int r_lo = rev_off != nullptr ? rev_off[row] : 0;
-  const int r_n = rev_off != nullptr ? rev_cnt[row] : 0;
   // the common case (bucket of <= 32 entries): order it once, lane p keeps the p-th smallest entry
   int s_j = 0;
   float s_qc = 0.f;
   if (r_n > 0 && r_n <= 32) {
-    const unsigned mine0 = lane < r_n ? static_cast<unsigned>(rev_list[r_lo + lane]) : 0xffffffffu;
-    unsigned mine = mine0;
+    unsigned mine = lane < r_n ? static_cast<unsigned>(rev_list[r_lo + lane]) : 0xffffffffu;
     for (int p = 0; p < r_n; ++p) {
       const unsigned e = __reduce_min_sync(0xffffffffu, mine);
       if (mine == e) mine = 0xffffffffu;  // entries are unique
@@ -600,24 +629,29 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
       }
     }
   }
-  for (int c0 = lane * 4; c0 < d; c0 += 128) {
+  // ---- D in segments of 128 columns (one float4 per lane); lanes beyond D only take part in the shuffles
+  for (int c0 = lane * 4; c0 - lane * 4 < d; c0 += 128) {
+    const bool ok = c0 < d;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ch = 0; ch < chunks; ++ch) {
-      const float4 p =
-          *reinterpret_cast<const float4*>(dx_partial + (static_cast<size_t>(ch) * m_pad + row) * d + c0);
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    const float* src = dx_partial + static_cast<size_t>(row) * d + c0;
+    const size_t slab = static_cast<size_t>(m_pad) * d;
+    if (ok) {
+      for (int ch = 0; ch < chunks; ++ch) {
+        const float4 p0 = *reinterpret_cast<const float4*>(src + ch * slab);
+        acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+      }
     }
     for (unsigned m = own_mask; m; m &= m - 1) {
       const int t = __ffs(m) - 1;
       const int col = __shfl_sync(0xffffffffu, my_col, t);
       const float qc = __shfl_sync(0xffffffffu, my_qc, t);
-      fma_row4(acc, qc, y_all + static_cast<size_t>(col) * y_ld, c0, y_lo);
+      if (ok) fma_row4(acc, qc, y_all + static_cast<size_t>(col) * y_ld, c0, y_lo);
     }
     if (r_n <= 32) {
       for (int p = 0; p < r_n; ++p) {
         const int j = __shfl_sync(0xffffffffu, s_j, p);
         const float qc = __shfl_sync(0xffffffffu, s_qc, p);
-        fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
+        if (ok) fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
       }
     }
     // larger buckets (hub rows): ascending entry order by repeated warp-wide selection of the smallest entry > last
@@ -632,23 +666,9 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict
       last = e;
       const int j = e / kp1;
       const float qc = -base * (s_eff + 2.f * w * gaps[j / b_local]) * opp_q_all[e];
-      fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
+      if (ok) fma_row4(acc, qc, y_all + static_cast<size_t>(j) * y_ld, c0, y_lo);
     }
-    if constexpr (std::is_same<OutT, float>::value) {
-      *reinterpret_cast<float4*>(dx_out + static_cast<size_t>(row) * d + c0) = acc;
-    } else if constexpr (std::is_same<OutT, __nv_bfloat16>::value) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dx_out + static_cast<size_t>(row) * d + c0) = pk;
-    } else {
-      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dx_out + static_cast<size_t>(row) * d + c0) = pk;
-    }
+    if (ok) store4<OutT>(dx_out + static_cast<size_t>(row) * d + c0, acc);
   }
 }
 

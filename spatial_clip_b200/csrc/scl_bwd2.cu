@@ -434,7 +434,9 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         if (packed[0] == 0x12345678u && packed[7] == 0x9abcdef0u) sts_v4(g_u32 + g_off, packed[0], packed[1], packed[2], packed[3]);
 #endif
       }
+#ifndef SCL_LAB_NO_FENCE
       fence_proxy_async();
+#endif
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(&bars.g_full);
@@ -498,9 +500,9 @@ static cudaError_t launch_bwd_rows_pair_t(const CUtensorMap& tm_rows, const CUte
                                           const float4* row_coef, const float4* col_coef, float* dx_partial,
                                           cudaStream_t stream) {
   const size_t smem = bwd_pair_smem_bytes(d, kSplit);
-  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state)
-  cudaError_t err = cudaFuncSetAttribute(bwd_rows_pair_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         231424);
+  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state --
+  // except under stream capture, where the eager warm-up launches have already set it)
+  cudaError_t err = set_max_dynamic_smem(bwd_rows_pair_kernel<kSplit>, 231424, stream);
   if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 127) / 128;
   const int n_tiles = (n_cols + kB2TileN - 1) / kB2TileN;

@@ -300,9 +300,9 @@ static cudaError_t launch_fwd_rowstats_pair_t(const CUtensorMap& tm_rows, const 
                                               const float* diag_z, int loc_lo, int loc_hi, int* rank_part,
                                               cudaStream_t stream) {
   const size_t smem = fwd_pair_smem_bytes(d);
-  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state)
-  cudaError_t err =
-      cudaFuncSetAttribute(fwd_rowstats_pair_kernel<kRank>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+  // opt in to > 48 KB dynamic shared memory (sticky per device; set on every launch so the library keeps no state --
+  // except under stream capture, where the eager warm-up launches have already set it)
+  cudaError_t err = set_max_dynamic_smem(fwd_rowstats_pair_kernel<kRank>, 231424, stream);
   if (err != cudaSuccess) return err;
   const int pairs = (m_rows + 255) / 256;
   const int n_tiles = (n_cols + kF2TileN - 1) / kF2TileN;

@@ -7,6 +7,15 @@
 
 namespace scl {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) unless `stream` is being captured into a CUDA graph
+template <typename Kernel>
+inline cudaError_t set_max_dynamic_smem(Kernel kernel, int bytes, cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) return cudaSuccess;
+  cudaGetLastError();
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 // ---- tensor-core kernels (CTA pairs, tcgen05 cta_group::2)
 // Column chunking for a grid of `units` row blocks (CTA pairs) over `slots` concurrently resident units: choose the
 // chunk count that minimises  waves * (tiles_per_chunk + per-CTA overhead) + chunks * chunk_cost  -- the launch

@@ -33,6 +33,7 @@ No CPU fallback exists: without libscl_b200.so, or with CPU tensors, ``forward``
 """
 from __future__ import annotations
 
+import atexit
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -40,7 +41,8 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss", "SpatialLossFromColumns"]
+__all__ = ["SpatialLoss", "ClipLoss", "GlobalMappingMultiPositiveClipLoss", "SpatialLossFromColumns",
+           "release_cuda_graphs"]
 
 _OPS = None
 
@@ -98,6 +100,7 @@ class _Cfg:
     group: object = None
     split: bool = False  # fp32-accurate mode: operands carried as bf16 hi/lo pairs
     want_ranks: bool = False  # also count every local image row's in-batch retrieval rank
+    use_graphs: bool = True  # replay forward / backward as CUDA graphs after two eager calls (_GraphedStep)
 
 
 def _col_mode(cfg: _Cfg) -> int:
@@ -116,85 +119,254 @@ def _col_mode(cfg: _Cfg) -> int:
 _NEUTRAL_LSE = 1.0e30  # column statistics of rows that carry no gradient: exp2(z s - 1e30) == 0
 
 
+def _forward_impl(ops, cfg: _Cfg, image_features, text_features, scale, image_tile_ids, text_tile_ids,
+                  neighbor_tile_ids, neighbor_alphas, positives, need_backward):
+    """Everything the forward launches, on the current stream, from plain tensors (no autograd state): used directly
+    (eager) and under CUDA-graph capture.  Returns (out4, lists_it, ranks, saved) with saved = the tensors backward
+    needs."""
+    b_local, d = image_features.shape
+    world, rank = cfg.world, cfg.rank
+    n = world * b_local
+    dev = image_features.device
+    mark = getattr(ops, "mark", lambda name, device: None)
+    mark("fwd:start", dev)
+    # ---- cap + bf16 copies of the local rows (the operands of gather_features, loss.py:21-65): one launch.
+    # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
+    # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
+    img_l, txt_l, img_c, txt_c, scalars = ops.prepare(image_features, text_features, scale, cfg.cap, split=cfg.split)
+    mark("fwd:prepared", dev)
+
+    # ---- exchanges (W > 1), all issued up front without waiting, in the order their consumers run: tile ids (one
+    # packed [2, B_l] record: both id vectors, losses.py:63-68) -> soft targets; gene features -> image-rows pass;
+    # image features -> text-rows pass.  Every phase waits only for the operand it reads, so the later exchanges
+    # run underneath the earlier phases' kernels.  The sequence of collectives depends on the configuration only.
+    ids = None
+    k = 0
+    waits = None
+    wait_ids = None
+    if positives is not None:
+        # soft targets resolved on the data side (positives.py): (columns int32, weights, probs) [B_l, K+1] of the
+        # image rows, optionally followed by the same three for the text rows.  No id exchange, no hash build.
+        k = positives[0].shape[1] - 1
+    elif cfg.kind == "spatial":
+        k = neighbor_tile_ids.shape[1]
+        same_ids = (image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
+                    and image_tile_ids.shape == text_tile_ids.shape)
+        img_ids = image_tile_ids.to(torch.int64).contiguous()
+        txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
+        if world > 1:
+            both, wait_ids = _all_gather_rows_async(torch.stack([img_ids, txt_ids]).reshape(1, 2, b_local), world,
+                                                    cfg.group)
+            ids_all = (both, None)  # [W, 2, B_l]; de-interleaved after the wait
+        else:
+            ids_all = (img_ids, txt_ids)
+        ids = [ids_all[0], ids_all[1], neighbor_tile_ids.to(torch.int64).contiguous(),
+               neighbor_alphas.to(torch.float32).contiguous(), same_ids]
+    if world > 1:
+        txt_all, wait_txt = _all_gather_rows_async(txt_c, world, cfg.group)
+        img_all, wait_img = _all_gather_rows_async(img_c, world, cfg.group)
+        if wait_ids is not None:
+            def wait_ids_and_split(w=wait_ids, rec=ids):
+                w()
+                rec[0], rec[1] = rec[0][:, 0].reshape(-1), rec[0][:, 1].reshape(-1)  # rank-major [N] each
+                if rec[4]:
+                    rec[1] = rec[0]
+            waits = (wait_ids_and_split, wait_txt, wait_img)
+        else:
+            waits = (None, wait_txt, wait_img)
+    else:
+        img_all, txt_all = img_c, txt_c
+
+    # ---- soft targets (losses.py:91-111), both fused similarity + online-LSE passes (losses.py:78-89,
+    # 113-121), row reductions and the loss scalars: one host call (one per phase when exchanges are in flight)
+    global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
+    c = 0.5 / (n if global_clip else b_local)
+    (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
+        img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
+        finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}),
+        **({"positives": positives} if positives is not None else {}))
+    mark("fwd:passes", dev)
+    if ranks is None:
+        ranks = torch.empty((0,), dtype=torch.int32, device=dev)
+    if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
+        # all-gather + fixed-order sum (bitwise identical on every rank, unlike an all-reduce tree)
+        sums6 = _all_gather_rows(sums6.reshape(1, 6), world, cfg.group).sum(dim=0)
+        out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
+    saved = (img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti, q_ti)
+    return out4, (col_it, w_it, q_it), ranks, saved, c
+
+
+def _backward_impl(ops, cfg: _Cfg, saved, go, c, d, need_i, need_t, out_dtypes):
+    """Everything the backward launches (see _forward_impl).  Returns (d_image or None, d_text or None)."""
+    (img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti, q_ti) = saved
+    world, rank = cfg.world, cfg.rank
+    b_local = img_l.shape[0]
+    n = world * b_local
+    mark = getattr(ops, "mark", lambda name, device: None)
+    mark("bwd:start", img_l.device)
+    mode = _col_mode(cfg)
+    global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
+
+    # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients.  Only when other ranks'
+    # rows reach the local features at all: with a non-differentiable gather and local_loss (mode 0) the
+    # reference's backward has no collective either, and none is issued here.
+    if world > 1 and mode != 0:
+        gap_rows = out4[1:2].reshape(1, 1)
+        (stats_i_all, stats_t_all, col_it_all, q_it_all, col_ti_all, q_ti_all, gaps) = ops.exchange_records(
+            [stats_i, stats_t, col_it, q_it, col_ti, q_ti, gap_rows], world,
+            lambda t: _all_gather_rows(t, world, cfg.group))
+        gaps = gaps.reshape(world)
+    elif world > 1:
+        # column statistics that switch the column-direction terms off (bwd_coeffs multiplies them by zero; the
+        # neutral LSE keeps the exponentials finite), this rank's gap in its slot, no opposite-direction lists
+        neutral = torch.zeros((n, 4), dtype=torch.float32, device=img_l.device)
+        neutral[:, 0] = _NEUTRAL_LSE
+        stats_i_all = stats_t_all = neutral
+        col_it_all = q_it_all = col_ti_all = q_ti_all = None
+        gaps = torch.zeros((world,), dtype=torch.float32, device=img_l.device)
+        gaps[rank:rank + 1] = out4[1:2]
+    else:
+        stats_i_all, stats_t_all = stats_i, stats_t
+        col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti
+        gaps = out4[1:2].contiguous()
+    mark("bwd:exchanged", img_l.device)
+
+    mult = float(world) if (global_clip and cfg.gather_with_grad) else 1.0
+    w = cfg.temp_reg_weight
+    d_img = d_txt = None
+    if need_i:
+        d_img = ops.backward_dir(img_l, txt_all, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
+                                 b_local, rank, gaps, scalars, go, c, w, mult, mode, out_dtypes[0], q_ti,
+                                 split=cfg.split)
+        mark("bwd:d_image", img_l.device)
+    if need_t:
+        d_txt = ops.backward_dir(txt_l, img_all, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
+                                 b_local, rank, gaps, scalars, go, c, w, mult, mode, out_dtypes[1], q_it,
+                                 split=cfg.split)
+        mark("bwd:d_text", img_l.device)
+    return d_img, d_txt
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA graphs: one replay per forward, one per backward
+# ------------------------------------------------------------------------------------------------
+class _GraphedStep:
+    """Forward and backward of ONE configuration (shapes, dtypes, flags, process group) captured as two CUDA graphs.
+
+    A step is ~25 kernel launches, four collectives and a few dozen small tensor operations: ~0.6 ms of host time at
+    one rank and ~1.1 ms with the exchanges (measured, bench.py host_enqueue_ms_per_step) -- more than the ~1 ms of
+    kernels a rank of an 8-GPU job runs.  The first ``WARMUP`` calls run eagerly (they also initialise the NCCL
+    communicator); the next one is captured -- inputs are copied into static buffers, results are cloned out -- and
+    every later call is two copies and one ``replay()``.  NCCL collectives are captured with the kernels.
+
+    The saved activations live in the graph's private pool and are overwritten by the next forward, so a backward must
+    follow ITS forward (the training loop's order); anything else raises."""
+
+    WARMUP = 2
+
+    def __init__(self):
+        self.calls = 0
+        self.generation = 0
+        self.pool = None
+        self.fwd = None  # (graph, static inputs, outputs)
+        self.bwd = None
+        self.fwd_launches = self.bwd_launches = 0
+        self.broken = False
+
+    @staticmethod
+    def _copy_in(static, fresh):
+        for s_t, f_t in zip(static, fresh):
+            if s_t is not None and s_t.data_ptr() != f_t.data_ptr():
+                s_t.copy_(f_t, non_blocking=True)
+
+
+_GRAPHS: Dict[tuple, _GraphedStep] = {}
+
+
+def release_cuda_graphs():
+    """Drop every captured step (graphs, static buffers).  Captured NCCL kernels keep their communicator busy, so this
+    must run BEFORE ``torch.distributed.destroy_process_group()`` (which otherwise waits for them forever); it is also
+    registered with ``atexit``, ahead of torch's own teardown."""
+    if _GRAPHS:
+        _GRAPHS.clear()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
+
+atexit.register(release_cuda_graphs)
+
+
+def _graph_key(cfg: _Cfg, tensors, flags):
+    sig = tuple((tuple(t.shape), t.dtype, t.device.index) if t is not None else None for t in tensors)
+    return (cfg.kind, cfg.rank, cfg.world, cfg.local_loss, cfg.gather_with_grad, cfg.cap, cfg.temp_reg_weight,
+            cfg.alpha_scale, id(cfg.group), cfg.split, cfg.want_ranks, sig, flags)
+
+
+def _graphs_usable(ops, cfg: _Cfg, tensors) -> bool:
+    if not cfg.use_graphs or not getattr(ops, "graph_capable", False):
+        return False
+    if not all(t is None or t.is_cuda for t in tensors):
+        return False
+    if ops.kernel_events is not None or getattr(ops, "timeline", None) is not None:
+        return False  # developer timing modes record events around individual launches
+    if cfg.world > 1 and dist.get_backend(cfg.group) != "nccl":
+        return False  # only NCCL collectives can be captured
+    return not torch.cuda.is_current_stream_capturing()  # (else: the caller is capturing the whole step already)
+
+
 class _ContrastiveLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, image_tile_ids, text_tile_ids, neighbor_tile_ids,
                 neighbor_alphas, cfg: _Cfg, positives=None):
         ops = _ops()
         b_local, d = image_features.shape
-        world, rank = cfg.world, cfg.rank
-        n = world * b_local
+        n = cfg.world * b_local
         dev = image_features.device
-
+        need_backward = any(ctx.needs_input_grad[:3])
         scale = logit_scale.detach().reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous()
         if hasattr(ops, "check_shapes"):
             ops.check_shapes(b_local, n, d, cfg.split, any(ctx.needs_input_grad[:2]))
+        img_in = image_features.detach().contiguous()
+        txt_in = text_features.detach().contiguous()
+        if txt_in.dtype != img_in.dtype:
+            txt_in = txt_in.to(img_in.dtype)
+        ins = [img_in, txt_in, scale, image_tile_ids, text_tile_ids, neighbor_tile_ids, neighbor_alphas]
+        ins += list(positives) if positives is not None else []
 
-        # ---- cap + bf16 copies of the local rows (the operands of gather_features, loss.py:21-65): one launch.
-        # *_l: the local rows as row operands, *_c: the same rows as column operands (identical tensors unless
-        # cfg.split, where rows are laid out (h|h|l) and columns (h|l|h), 3 D wide)
-        mark = getattr(ops, "mark", lambda name, device: None)
-        mark("fwd:start", dev)
-        img_l, txt_l, img_c, txt_c, scalars = ops.prepare(
-            image_features.detach().contiguous(), text_features.detach().contiguous(), scale, cfg.cap, split=cfg.split)
-        mark("fwd:prepared", dev)
-
-        # ---- exchanges (W > 1), all issued up front without waiting, in the order their consumers run: tile ids (one
-        # packed [2, B_l] record: both id vectors, losses.py:63-68) -> soft targets; gene features -> image-rows pass;
-        # image features -> text-rows pass.  Every phase waits only for the operand it reads, so the later exchanges
-        # run underneath the earlier phases' kernels.  The sequence of collectives depends on the configuration only.
-        ids = None
-        k = 0
-        waits = None
-        wait_ids = None
-        if positives is not None:
-            # soft targets resolved on the data side (positives.py): (columns int32, weights, probs) [B_l, K+1] of the
-            # image rows, optionally followed by the same three for the text rows.  No id exchange, no hash build.
-            k = positives[0].shape[1] - 1
-        elif cfg.kind == "spatial":
-            k = neighbor_tile_ids.shape[1]
-            same_ids = (image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
-                        and image_tile_ids.shape == text_tile_ids.shape)
-            img_ids = image_tile_ids.to(torch.int64).contiguous()
-            txt_ids = img_ids if same_ids else text_tile_ids.to(torch.int64).contiguous()
-            if world > 1:
-                both, wait_ids = _all_gather_rows_async(torch.stack([img_ids, txt_ids]).reshape(1, 2, b_local), world,
-                                                        cfg.group)
-                ids_all = (both, None)  # [W, 2, B_l]; de-interleaved after the wait
-            else:
-                ids_all = (img_ids, txt_ids)
-            ids = [ids_all[0], ids_all[1], neighbor_tile_ids.to(torch.int64).contiguous(),
-                   neighbor_alphas.to(torch.float32).contiguous(), same_ids]
-        if world > 1:
-            txt_all, wait_txt = _all_gather_rows_async(txt_c, world, cfg.group)
-            img_all, wait_img = _all_gather_rows_async(img_c, world, cfg.group)
-            if wait_ids is not None:
-                def wait_ids_and_split(w=wait_ids, rec=ids):
-                    w()
-                    rec[0], rec[1] = rec[0][:, 0].reshape(-1), rec[0][:, 1].reshape(-1)  # rank-major [N] each
-                    if rec[4]:
-                        rec[1] = rec[0]
-                waits = (wait_ids_and_split, wait_txt, wait_img)
-            else:
-                waits = (None, wait_txt, wait_img)
+        step = None
+        if positives is None and _graphs_usable(ops, cfg, ins):
+            same_ids = cfg.kind == "spatial" and image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
+            key = _graph_key(cfg, ins, (need_backward, same_ids, tuple(ctx.needs_input_grad[:3])))
+            step = _GRAPHS.setdefault(key, _GraphedStep())
+            if step.broken:
+                step = None
+        if step is not None:
+            step.calls += 1
+            if step.calls <= step.WARMUP:
+                step = None
+        if step is None:
+            out4, lists, ranks, saved, c = _forward_impl(ops, cfg, img_in, txt_in, scale, image_tile_ids, text_tile_ids,
+                                                         neighbor_tile_ids, neighbor_alphas, positives, need_backward)
         else:
-            img_all, txt_all = img_c, txt_c
-
-        # ---- soft targets (losses.py:91-111), both fused similarity + online-LSE passes (losses.py:78-89,
-        # 113-121), row reductions and the loss scalars: one host call (one per phase when exchanges are in flight)
-        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
-        c = 0.5 / (n if global_clip else b_local)
-        (col_it, w_it, q_it), (col_ti, w_ti, q_ti), stats_i, stats_t, sums6, out4, ranks = ops.forward_all(
-            img_l, txt_l, img_all, txt_all, scalars, ids, b_local, rank, k, cfg.alpha_scale, c, cfg.temp_reg_weight,
-            finalize_scalars=not global_clip, want_ranks=cfg.want_ranks, **({"waits": waits} if waits else {}),
-            **({"positives": positives} if positives is not None else {}))
-        mark("fwd:passes", dev)
-        if ranks is None:
-            ranks = torch.empty((0,), dtype=torch.int32, device=dev)
-        if global_clip:  # every rank evaluates the full N x N loss (loss.py:120-121)
-            # all-gather + fixed-order sum (bitwise identical on every rank, unlike an all-reduce tree)
-            sums6 = _all_gather_rows(sums6.reshape(1, 6), world, cfg.group).sum(dim=0)
-            out4 = ops.loss_scalars(sums6, scalars, c, cfg.temp_reg_weight)
+            if step.fwd is None:  # capture
+                static = [t.clone() if t is not None else None for t in ins]
+                if cfg.kind == "spatial" and image_tile_ids.data_ptr() == text_tile_ids.data_ptr():
+                    static[4] = static[3]  # keep the aliasing the capture-time control flow saw
+                launches0 = ops.launches
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(graph, pool=step.pool, capture_error_mode="thread_local"):
+                    outs = _forward_impl(ops, cfg, static[0], static[1], static[2], static[3], static[4], static[5],
+                                         static[6], None, need_backward)
+                step.pool = graph.pool()
+                step.fwd = (graph, static, outs)
+                step.fwd_launches = ops.launches - launches0
+            else:
+                step._copy_in(step.fwd[1], ins)
+                ops.launches += step.fwd_launches
+            step.fwd[0].replay()
+            step.generation += 1
+            out4, lists, ranks, saved, c = step.fwd[2]  # (lists / ranks: "of the last call", static buffers)
 
         ctx.cfg = cfg
         ctx.d = d
@@ -202,8 +374,13 @@ class _ContrastiveLossFn(torch.autograd.Function):
         ctx.in_dtypes = (image_features.dtype, text_features.dtype, logit_scale.dtype)
         ctx.scale_shape = logit_scale.shape
         ctx.scale_device = logit_scale.device
-        ctx.save_for_backward(img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti,
-                              q_ti)
+        ctx.step = step
+        ctx.generation = step.generation if step is not None else 0
+        if step is None:
+            ctx.save_for_backward(*saved)
+        else:
+            ctx.saved_static = saved  # graph-pool buffers: valid until the next forward of this configuration
+        col_it, w_it, q_it = lists
         if positives is not None:  # the caller already holds them: do not hand inputs back as outputs
             col_it, w_it, q_it = (t.new_empty((0,)) for t in (col_it, w_it, q_it))
         ctx.mark_non_differentiable(col_it, w_it, q_it, ranks)
@@ -213,54 +390,35 @@ class _ContrastiveLossFn(torch.autograd.Function):
     def backward(ctx, grad_loss, *_unused):
         ops = _ops()
         cfg: _Cfg = ctx.cfg
-        (img_l, txt_l, img_all, txt_all, scalars, stats_i, stats_t, out4, col_it, q_it, col_ti, q_ti) = ctx.saved_tensors
-        world, rank = cfg.world, cfg.rank
-        b_local, d = img_l.shape[0], ctx.d
-        n = world * b_local
-        go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
-        mark = getattr(ops, "mark", lambda name, device: None)
-        mark("bwd:start", img_l.device)
-        mode = _col_mode(cfg)
-        global_clip = cfg.kind == "clip" and world > 1 and not cfg.local_loss
-
-        # ---- exchange per-row statistics instead of reduce-scattering [N, D] gradients.  Only when other ranks'
-        # rows reach the local features at all: with a non-differentiable gather and local_loss (mode 0) the
-        # reference's backward has no collective either, and none is issued here.
-        if world > 1 and mode != 0:
-            gap_rows = out4[1:2].reshape(1, 1)
-            (stats_i_all, stats_t_all, col_it_all, q_it_all, col_ti_all, q_ti_all, gaps) = ops.exchange_records(
-                [stats_i, stats_t, col_it, q_it, col_ti, q_ti, gap_rows], world,
-                lambda t: _all_gather_rows(t, world, cfg.group))
-            gaps = gaps.reshape(world)
-        elif world > 1:
-            # column statistics that switch the column-direction terms off (bwd_coeffs multiplies them by zero; the
-            # neutral LSE keeps the exponentials finite), this rank's gap in its slot, no opposite-direction lists
-            neutral = torch.zeros((n, 4), dtype=torch.float32, device=img_l.device)
-            neutral[:, 0] = _NEUTRAL_LSE
-            stats_i_all = stats_t_all = neutral
-            col_it_all = q_it_all = col_ti_all = q_ti_all = None
-            gaps = torch.zeros((world,), dtype=torch.float32, device=img_l.device)
-            gaps[rank:rank + 1] = out4[1:2]
-        else:
-            stats_i_all, stats_t_all = stats_i, stats_t
-            col_it_all, q_it_all, col_ti_all, q_ti_all = col_it, q_it, col_ti, q_ti
-            gaps = out4[1:2].contiguous()
-
-        mark("bwd:exchanged", img_l.device)
-        mult = float(world) if (global_clip and cfg.gather_with_grad) else 1.0
-        w = cfg.temp_reg_weight
+        step: Optional[_GraphedStep] = ctx.step
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        d_img = d_txt = d_scale = None
-        if need_i:
-            d_img = ops.backward_dir(img_l, txt_all, stats_i, stats_t_all, col_it, q_it, col_ti_all, q_ti_all,
-                                     b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[0], q_ti,
-                                     split=cfg.split)
-            mark("bwd:d_image", img_l.device)
-        if need_t:
-            d_txt = ops.backward_dir(txt_l, img_all, stats_t, stats_i_all, col_ti, q_ti, col_it_all, q_it_all,
-                                     b_local, rank, gaps, scalars, go, ctx.c, w, mult, mode, ctx.in_dtypes[1], q_it,
-                                     split=cfg.split)
-            mark("bwd:d_text", img_l.device)
+        go = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        if step is None:
+            saved = ctx.saved_tensors
+            d_img, d_txt = _backward_impl(ops, cfg, saved, go, ctx.c, ctx.d, need_i, need_t, ctx.in_dtypes)
+            out4 = saved[7]
+        else:
+            if ctx.generation != step.generation:
+                raise RuntimeError("spatial_clip_b200: backward() of a loss whose CUDA-graph buffers were overwritten by a "
+                                   "later forward of the same configuration; call backward before the next forward, or "
+                                   "construct the loss with cuda_graphs=False")
+            saved = ctx.saved_static
+            out4 = saved[7]
+            if step.bwd is None:  # capture
+                go_static = go.clone()
+                launches0 = ops.launches
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(go.device)
+                with torch.cuda.graph(graph, pool=step.pool, capture_error_mode="thread_local"):
+                    outs = _backward_impl(ops, cfg, saved, go_static, ctx.c, ctx.d, need_i, need_t, ctx.in_dtypes)
+                step.bwd = (graph, [go_static], outs)
+                step.bwd_launches = ops.launches - launches0
+            else:
+                step._copy_in(step.bwd[1], [go])
+                ops.launches += step.bwd_launches
+            step.bwd[0].replay()
+            d_img, d_txt = (t.clone() if t is not None else None for t in step.bwd[2])
+        d_scale = None
         if need_s:
             # straight-through cap: d s_eff / d s == 1 even when clipped (losses.py:73-76)
             d_scale = (go * out4[2]).to(device=ctx.scale_device, dtype=ctx.in_dtypes[2]).reshape(ctx.scale_shape)
@@ -272,7 +430,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class _LossBase(nn.Module):
     def __init__(self, local_loss, gather_with_grad, rank, world_size, use_horovod, precision="bf16",
-                 track_retrieval_ranks=False):
+                 track_retrieval_ranks=False, cuda_graphs=True):
         super().__init__()
         if use_horovod:
             raise NotImplementedError("horovod exchange is out of scope; use torch.distributed (NCCL)")
@@ -288,6 +446,10 @@ class _LossBase(nn.Module):
         # metrics.py:22-36); Recall@k = (ranks < k).float().mean(), see spatial_clip_b200/metrics.py
         self.track_retrieval_ranks = bool(track_retrieval_ranks)
         self.last_retrieval_ranks = None
+        # After two eager calls per configuration, forward and backward are replayed as CUDA graphs (kernels AND the
+        # NCCL exchanges): the step's host cost drops from ~1 ms to a few copies and two replays.  Requires the training
+        # loop's order (each backward before the next forward of the same shapes); set False otherwise.
+        self.cuda_graphs = bool(cuda_graphs)
         self.local_loss = bool(local_loss)
         self.gather_with_grad = bool(gather_with_grad)
         self.use_horovod = False
@@ -338,8 +500,9 @@ class SpatialLoss(_LossBase):
                  world_size: Optional[int] = None, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
                  float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16",
-                 track_retrieval_ranks: bool = False):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks)
+                 track_retrieval_ranks: bool = False, cuda_graphs: bool = True):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks,
+                         cuda_graphs)
         self.cap_logit_scale = cap_logit_scale
         self.temp_reg_weight = float(temp_reg_weight or 0.0)
         self.float32_logits = float32_logits  # logits are always fp32 on chip
@@ -359,7 +522,7 @@ class SpatialLoss(_LossBase):
             raise ValueError("tile ids must be [B] and neighbour ids / alphas [B, K]")
         cfg = _Cfg("spatial", self.rank, self.world_size, self.local_loss, self.gather_with_grad,
                    self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
-                   self.precision == "fp32", self.track_retrieval_ranks)
+                   self.precision == "fp32", self.track_retrieval_ranks, self.cuda_graphs)
         loss, col, w, q, ranks = _ContrastiveLossFn.apply(image_features, text_features,
                                                           self._scale_tensor(logit_scale, image_features),
                                                           image_tile_ids, text_tile_ids, neighbor_tile_ids,
@@ -475,7 +638,7 @@ class SpatialLossFromColumns(SpatialLoss):
         self._list_check.submit(flags)
         cfg = _Cfg("spatial", rank, world, self.local_loss, self.gather_with_grad,
                    self.cap_logit_scale, self.temp_reg_weight, self.neighbor_alpha_scale, self.process_group,
-                   self.precision == "fp32", self.track_retrieval_ranks)
+                   self.precision == "fp32", self.track_retrieval_ranks, self.cuda_graphs)
         loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,
                                                         self._scale_tensor(logit_scale, image_features), None, None,
                                                         None, None, cfg, pos)
@@ -489,8 +652,9 @@ class ClipLoss(_LossBase):
 
     def __init__(self, local_loss: bool = False, gather_with_grad: bool = False, cache_labels: bool = False,
                  rank: Optional[int] = None, world_size: Optional[int] = None, use_horovod: bool = False,
-                 precision: str = "bf16", track_retrieval_ranks: bool = False):
-        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks)
+                 precision: str = "bf16", track_retrieval_ranks: bool = False, cuda_graphs: bool = True):
+        super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, precision, track_retrieval_ranks,
+                         cuda_graphs)
         self.cache_labels = cache_labels  # labels are implicit (the diagonal); nothing to cache
 
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: torch.Tensor,
@@ -498,7 +662,7 @@ class ClipLoss(_LossBase):
         self._check_features(image_features, text_features, logit_bias)
         image_features, text_features = self._kernel_dtype(image_features), self._kernel_dtype(text_features)
         cfg = _Cfg("clip", self.rank, self.world_size, self.local_loss, self.gather_with_grad, None, 0.0, 1.0,
-                   self.process_group, self.precision == "fp32", self.track_retrieval_ranks)
+                   self.process_group, self.precision == "fp32", self.track_retrieval_ranks, self.cuda_graphs)
         loss, _, _, _, ranks = _ContrastiveLossFn.apply(image_features, text_features,
                                                         self._scale_tensor(logit_scale, image_features), None, None,
                                                         None, None, cfg, None)
@@ -513,9 +677,10 @@ class GlobalMappingMultiPositiveClipLoss(SpatialLoss):
                  rank: Optional[int] = 0, world_size: Optional[int] = 1, use_horovod: bool = False,
                  cap_logit_scale: Optional[float] = None, temp_reg_weight: float = 0.0,
                  float32_logits: bool = False, neighbor_alpha_scale: float = 1.0, precision: str = "bf16",
-                 track_retrieval_ranks: bool = False):
+                 track_retrieval_ranks: bool = False, cuda_graphs: bool = True):
         super().__init__(local_loss, gather_with_grad, rank, world_size, use_horovod, cap_logit_scale,
-                         temp_reg_weight, float32_logits, neighbor_alpha_scale, precision, track_retrieval_ranks)
+                         temp_reg_weight, float32_logits, neighbor_alpha_scale, precision, track_retrieval_ranks,
+                         cuda_graphs)
         self.cache_labels = cache_labels
 
     def forward(self, image_features, text_features, image_tile_ids, text_tile_ids, neighbor_tile_ids,

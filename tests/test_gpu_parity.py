@@ -528,3 +528,77 @@ def test_backward_is_bitwise_reproducible(ops):
     assert np.abs(gi[7] - orc.d_image[7]).max() <= 5e-3 * np.abs(orc.d_image[7]).max()
     gt = first[2].cpu().numpy()
     assert np.abs(gt - orc.d_text).max() <= 5e-3 * np.abs(orc.d_text).max()
+
+
+# ---------------------------------------------------------------- CUDA-graph replay of the step
+@pytest.mark.parametrize("kind", ["spatial", "spatial_same_ids", "clip"])
+def test_graph_replay_is_bitwise_identical_to_eager(ops, kind):
+    """After two eager calls per configuration the modules replay forward and backward as CUDA graphs: same kernels
+    on the same values, so every step must equal the eager module bit for bit -- with inputs that change from step to
+    step and live at different addresses."""
+    from spatial_clip_b200 import ClipLoss, SpatialLoss
+
+    n, d, k = 1500, 256, 8
+    cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
+               neighbor_alpha_scale=0.5, float32_logits=True)
+    if kind == "clip":
+        graphed, eager = ClipLoss(), ClipLoss(cuda_graphs=False)
+    else:
+        graphed, eager = SpatialLoss(**cfg), SpatialLoss(**cfg, cuda_graphs=False)
+    keep = []
+    for step in range(6):
+        b = make_spot_batch(n=n, d=d, k=k, seed=300 + step, dup_frac=0.02, self_loops=True)
+        res = []
+        for mod in (graphed, eager):
+            img = b.image_features.cuda().requires_grad_(True)
+            txt = b.text_features.cuda().requires_grad_(True)
+            s = torch.tensor(30.0 + step, device="cuda", requires_grad=True)
+            keep.append((img, txt))  # keep earlier inputs alive so that later ones get fresh addresses
+            if kind == "clip":
+                out = mod(img, txt, s)
+            else:
+                ids = b.tile_ids.cuda()
+                tids = ids if kind == "spatial_same_ids" else ids.clone()
+                out = mod(img, txt, s, ids, tids, b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())
+            loss = out["contrastive_loss"]
+            (loss * (1.0 + 0.5 * step)).backward()  # a different upstream gradient every step
+            torch.cuda.synchronize()
+            res.append((loss.detach().clone(), img.grad.clone(), txt.grad.clone(), s.grad.clone()))
+        for a, c in zip(*res):
+            assert torch.equal(a, c), (kind, step)
+    from spatial_clip_b200 import losses
+
+    assert any(st.fwd is not None and st.bwd is not None for st in losses._GRAPHS.values()), "no graph was captured"
+
+
+def test_graph_buffers_guard_against_out_of_order_backward(ops):
+    from spatial_clip_b200 import ClipLoss
+
+    mod = ClipLoss()
+    b = make_spot_batch(n=512, d=128, k=0, seed=5)
+
+    def fwd():
+        img = b.image_features.cuda().requires_grad_(True)
+        txt = b.text_features.cuda().requires_grad_(True)
+        return mod(img, txt, torch.tensor(20.0, device="cuda", requires_grad=True))["contrastive_loss"]
+
+    for _ in range(3):
+        fwd().backward()
+    first = fwd()
+    second = fwd()  # overwrites the graph's saved activations
+    with pytest.raises(RuntimeError, match="overwritten"):
+        first.backward()
+    second.backward()
+
+
+def test_no_grad_forward_replays_too(ops):
+    from spatial_clip_b200 import ClipLoss
+
+    mod, ref = ClipLoss(), ClipLoss(cuda_graphs=False)
+    for step in range(5):
+        b = make_spot_batch(n=700, d=128, k=0, seed=40 + step)
+        with torch.no_grad():
+            s = torch.tensor(25.0, device="cuda")
+            a = mod(b.image_features.cuda(), b.text_features.cuda(), s)["contrastive_loss"]
+            c = ref(b.image_features.cuda(), b.text_features.cuda(), s)["contrastive_loss"]
+        assert torch.equal(a, c)

@@ -18,11 +18,8 @@ sys.path.insert(0, str(ROOT))
 
 VARIANTS = {
     "base": [],
-    "no_lds": ["-DSCL_LAB_NO_LDS"],
+    "no_fence": ["-DSCL_LAB_NO_FENCE"],
     "no_sts": ["-DSCL_LAB_NO_STS"],
-    "one_ex2": ["-DSCL_LAB_ONE_EX2"],
-    "no_lds_no_sts": ["-DSCL_LAB_NO_LDS", "-DSCL_LAB_NO_STS"],
-    "no_lds_no_sts_one_ex2": ["-DSCL_LAB_NO_LDS", "-DSCL_LAB_NO_STS", "-DSCL_LAB_ONE_EX2"],
     "no_epi": ["-DSCL_LAB_NO_EPI"],
 }
 
