@@ -322,7 +322,7 @@ def run_ours(args):
                 nbr=loc.neighbor_tile_ids.pin_memory(), alpha=loc.neighbor_alphas.pin_memory())
     dev_in = {k: v.to(dev) for k, v in host.items()}
     scale = torch.tensor(SCALE, device=dev, requires_grad=True)
-    mod = SpatialLoss(**SPATIAL_CFG, precision=args.precision)
+    mod = SpatialLoss(**SPATIAL_CFG, precision=args.precision, cuda_graphs=not args.no_graphs)
     split = args.precision == "fp32"
     ops = losses._ops()
 
@@ -489,10 +489,10 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
 
+    del loss, g_img, g_txt
     losses.release_cuda_graphs()  # captured NCCL kernels must go before the process group does
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     pk = peaks()
@@ -540,7 +540,7 @@ def run_ours(args):
         "loss": loss_val,
         "e2e": {"value": N_GLOBAL / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "steps": e2e_steps, "pipeline": e2e_note},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "cuda_graphs": not args.no_graphs,
         "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "bwd_rows_pair_kernel", "achieved": achieved, "peak": pk["burst"],
@@ -569,9 +569,28 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
                          "sample": cpu_sample_text(cpu)},
     }
-    print(json.dumps(line))
-    if world > 1:
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Tear the process group down, but never let a teardown that waits on another rank hold the job: the result is
+    out already, so after 20 s the process exits on its own (exit code 0)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    def bail():
+        sys.stdout.flush()
+        os._exit(0)
+
+    t = threading.Timer(20.0, bail)
+    t.daemon = True
+    t.start()
+    try:
         dist.destroy_process_group()
+    finally:
+        t.cancel()
 
 
 def main():
@@ -580,6 +599,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)  # 10 warm-up + 50 timed
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-graphs", action="store_true", help="run every step eagerly (no CUDA-graph replay)")
     ap.add_argument("--timeline", action="store_true", help="add the per-phase GPU times of one step to the JSON line")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="fp32: the fp32-accurate mode (bf16 hi/lo operand pairs), BASELINE configs[4]'s 'fp32 vs bf16'")

@@ -586,7 +586,7 @@ __device__ __forceinline__ void store4(OutT* dst, const float4& v) {
   }
 }
 template <typename OutT>
-__global__ void __launch_bounds__(256, 4) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
+__global__ void __launch_bounds__(256) bwd_gather_kernel(const float* __restrict__ dx_partial, int chunks, int m_pad,
                                                          int m_rows, int d, const __nv_bfloat16* __restrict__ y_all,
                                                          const int* __restrict__ pos_col,
                                                          const float* __restrict__ pos_q, int kp1, int b_local, int rank,

@@ -287,10 +287,23 @@ def release_cuda_graphs():
     """Drop every captured step (graphs, static buffers).  Captured NCCL kernels keep their communicator busy, so this
     must run BEFORE ``torch.distributed.destroy_process_group()`` (which otherwise waits for them forever); it is also
     registered with ``atexit``, ahead of torch's own teardown."""
-    if _GRAPHS:
-        _GRAPHS.clear()
-        if torch.cuda.is_available():
-            torch.cuda.synchronize()
+    if not _GRAPHS:
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for step in _GRAPHS.values():
+        # autograd nodes of the last step may still hold the step object: reset the graphs themselves
+        step.broken = True
+        for captured in (step.fwd, step.bwd):
+            if captured is not None:
+                try:
+                    captured[0].reset()
+                except Exception:
+                    pass
+        step.fwd = step.bwd = step.pool = None
+    _GRAPHS.clear()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 atexit.register(release_cuda_graphs)
@@ -398,7 +411,7 @@ class _ContrastiveLossFn(torch.autograd.Function):
             d_img, d_txt = _backward_impl(ops, cfg, saved, go, ctx.c, ctx.d, need_i, need_t, ctx.in_dtypes)
             out4 = saved[7]
         else:
-            if ctx.generation != step.generation:
+            if step.broken or ctx.generation != step.generation:
                 raise RuntimeError("spatial_clip_b200: backward() of a loss whose CUDA-graph buffers were overwritten by a "
                                    "later forward of the same configuration; call backward before the next forward, or "
                                    "construct the loss with cuda_graphs=False")
