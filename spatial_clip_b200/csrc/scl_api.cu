@@ -154,9 +154,10 @@ int scl_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr
     return SCL_ERR_INVALID_ARG;
   if (k > 0 && (all_ids == nullptr || nbr_ids == nullptr || nbr_alpha == nullptr || workspace == nullptr))
     return SCL_ERR_INVALID_ARG;
+  if (k > 31) return SCL_ERR_INVALID_ARG;
   return cuda_rc(scl::launch_build_positives(all_ids, n_global, nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank,
-                                             workspace, workspace_bytes, pos_col, pos_w, pos_q,
-                                             static_cast<cudaStream_t>(stream)));
+                                             workspace, workspace_bytes, pos_col, pos_w, pos_q, nullptr, nullptr,
+                                             nullptr, nullptr, static_cast<cudaStream_t>(stream)));
 }
 
 int scl_fwd_rowstats(const void* x_rows, int m_rows, const void* y_cols, int n_cols, int d, const float* scalars3,
@@ -308,7 +309,7 @@ size_t scl_fwd_workspace_bytes(int b_local, int n_global, int d, int k) {
   scl_plan p;
   if (scl_fwd_plan(b_local, n_global, d, &p) != SCL_OK) return 0;
   const size_t partial = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 16);
-  const size_t hash = k > 0 ? align256(scl::positives_hash_bytes(n_global)) : 0;
+  const size_t hash = k > 0 ? align256(scl::positives_hash_bytes(n_global)) + 256 : 0;  // + the ids-differ flag
   // + the retrieval-rank work areas (rank partials, own-pair similarities); small, so always included
   const size_t ranks = align256(static_cast<size_t>(p.n_slots) * p.m_pad * 4) + align256(static_cast<size_t>(p.m_pad) * 4);
   return 2 * partial + hash + ranks;
@@ -327,7 +328,7 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
   void* part_t = ws + partial_bytes;
   void* hash = ws + 2 * partial_bytes;
   const size_t hash_bytes = a->k > 0 ? scl::positives_hash_bytes(a->n_global) : 0;
-  char* rank_ws = ws + 2 * partial_bytes + (a->k > 0 ? align256(hash_bytes) : 0);
+  char* rank_ws = ws + 2 * partial_bytes + (a->k > 0 ? align256(hash_bytes) + 256 : 0);
   int32_t* rank_partial = reinterpret_cast<int32_t*>(rank_ws);
   float* diag_z = reinterpret_cast<float*>(rank_ws + align256(static_cast<size_t>(p.n_slots) * p.m_pad * 4));
   // phases (0 = everything): 1 soft targets (needs the gathered ids), 2 image-rows pass (needs txt_all),
@@ -339,8 +340,17 @@ int scl_fwd_all(const scl_fwd_args* a, void* stream) {
                              a->rank, a->k > 0 ? hash : nullptr, hash_bytes, a->col_it, a->w_it, a->q_it, stream);
     if (rc != SCL_OK) return rc;
     if (!a->same_ids && a->k > 0) {
-      rc = scl_build_positives(a->img_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k,
-                               a->alpha_scale, a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti, stream);
+      // text rows resolve their neighbours in the IMAGE id map.  The reference's loader makes the two id vectors
+      // equal (as separate tensors), so a device flag decides: identical vectors -> copy the lists just built
+      // (the hash kernels return at once), otherwise build them.  No host synchronisation either way.
+      if (a->img_ids_all == nullptr || a->txt_ids_all == nullptr) return SCL_ERR_INVALID_ARG;
+      int* differ = reinterpret_cast<int*>(static_cast<char*>(hash) + align256(hash_bytes));
+      rc = cuda_rc(scl::launch_ids_differ(a->img_ids_all, a->txt_ids_all, a->n_global, differ,
+                                          static_cast<cudaStream_t>(stream)));
+      if (rc != SCL_OK) return rc;
+      rc = cuda_rc(scl::launch_build_positives(a->img_ids_all, a->n_global, a->nbr_ids, a->nbr_alpha, a->b_local, a->k,
+                                               a->alpha_scale, a->rank, hash, hash_bytes, a->col_ti, a->w_ti, a->q_ti,
+                                               differ, a->col_it, a->w_it, a->q_it, static_cast<cudaStream_t>(stream)));
       if (rc != SCL_OK) return rc;
     }
   }

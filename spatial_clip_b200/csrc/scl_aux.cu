@@ -181,9 +181,10 @@ __global__ void hash_clear_kernel(long long* keys, int* vals, uint32_t cap) {
   }
 }
 // "last index wins" (dict comprehension, losses.py:92-93) == max index per key
-__global__ void hash_insert_kernel(const long long* __restrict__ ids, int n, long long* keys, int* vals, uint32_t cap) {
+__global__ void hash_insert_kernel(const long long* __restrict__ ids, int n, long long* keys, int* vals, uint32_t cap,
+                                   const int* __restrict__ run_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || (run_flag != nullptr && *run_flag == 0)) return;
   const long long id = ids[i];
   if (id == kEmptyKey) {  // the one key that collides with the sentinel lives in the extra slot
     atomicMax(&vals[cap], i);
@@ -212,66 +213,155 @@ __device__ __forceinline__ int hash_lookup(long long id, const long long* __rest
     slot = (slot + 1) & (cap - 1);
   }
 }
-// One thread per local row.  Slot 0 is the row's own column rank*B_l + i with weight 1 (losses.py:94-98);
-// neighbour slots are visited in k order, skipped when alpha*scale <= 0 or the id is not in the global
-// batch, and merged (fp32 +=) into the slot already holding the same column (losses.py:100-108).
-__global__ void build_ell_kernel(const long long* __restrict__ nbr_ids, const float* __restrict__ nbr_alpha,
-                                 int b_local, int k, float alpha_scale, int rank, const long long* __restrict__ keys,
-                                 const int* __restrict__ vals, uint32_t cap, int* __restrict__ pos_col,
-                                 float* __restrict__ pos_w, float* __restrict__ pos_q) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b_local) return;
+// G lanes per local row (G = 8 / 16 / 32 >= k), lane s = neighbour slot s.  Slot 0 of the output is the row's own
+// column rank*B_l + i with weight 1 (losses.py:94-98); neighbour slots are skipped when alpha*scale <= 0 or the id is
+// not in the global batch, and merged (fp32 +=, in k order) into the slot already holding the same column
+// (losses.py:100-108).  The K hash probes of a row run in parallel; the order-sensitive parts (which slot is a
+// column's first touch, the fp32 accumulation order, the L1 norm) are evaluated with shuffles in exactly the
+// sequential order of the reference, so weights and probabilities are bit-identical to the one-thread-per-row form.
+template <int G>
+__global__ void __launch_bounds__(256) build_ell_kernel(const long long* __restrict__ nbr_ids,
+                                                        const float* __restrict__ nbr_alpha, int b_local, int k,
+                                                        float alpha_scale, int rank, const long long* __restrict__ keys,
+                                                        const int* __restrict__ vals, uint32_t cap,
+                                                        int* __restrict__ pos_col, float* __restrict__ pos_w,
+                                                        float* __restrict__ pos_q, const int* __restrict__ copy_flag,
+                                                        const int* __restrict__ src_col, const float* __restrict__ src_w,
+                                                        const float* __restrict__ src_q) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / G;          // local row
+  const int s = tid % G;          // neighbour slot of this lane
+  const int lane = threadIdx.x & 31;
+  const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(G - 1));
+  const int g0 = lane & ~(G - 1);  // first lane of this row's group
   const int kp1 = k + 1;
-  int* col = pos_col + static_cast<size_t>(i) * kp1;
-  float* w = pos_w + static_cast<size_t>(i) * kp1;
-  float* q = pos_q + static_cast<size_t>(i) * kp1;
-  col[0] = rank * b_local + i;
-  w[0] = 1.0f;
-  int cnt = 1;
-  for (int s = 0; s < k; ++s) {
-    float a = __fmul_rn(nbr_alpha[static_cast<size_t>(i) * k + s], alpha_scale);
-    a = fmaxf(a, 0.f);
-    if (!(a > 0.f)) continue;
-    const int c = hash_lookup(nbr_ids[static_cast<size_t>(i) * k + s], keys, vals, cap);
-    if (c < 0) continue;
-    int hit = -1;
-    for (int t = 0; t < cnt; ++t)
-      if (col[t] == c) hit = t;
-    if (hit >= 0) {
-      w[hit] = __fadd_rn(w[hit], a);
-    } else {
-      col[cnt] = c;
-      w[cnt] = a;
-      ++cnt;
-    }
+  const bool row_ok = i < b_local;
+  if (copy_flag != nullptr && *copy_flag == 0) {
+    // the two id vectors are identical: this direction's lists equal the other direction's (already built)
+    if (row_ok)
+      for (int t = s; t < kp1; t += G) {
+        const size_t o = static_cast<size_t>(i) * kp1 + t;
+        pos_col[o] = src_col[o];
+        pos_w[o] = src_w[o];
+        pos_q[o] = src_q[o];
+      }
+    return;
   }
-  float tot = 0.f;
-  for (int t = 0; t < cnt; ++t) tot = __fadd_rn(tot, w[t]);
-  const float inv = 1.f / fmaxf(tot, 1e-12f);  // F.normalize(p=1) eps, losses.py:110-111
-  for (int t = 0; t < cnt; ++t) q[t] = w[t] * inv;
-  for (int t = cnt; t < kp1; ++t) {
-    col[t] = -1;
-    w[t] = 0.f;
-    q[t] = 0.f;
+  const int own = rank * b_local + i;
+  // ---- this lane's neighbour: scaled alpha and the column its id maps to (-1: not in the global batch)
+  float a = 0.f;
+  int c = -1;
+  if (row_ok && s < k) {
+    a = fmaxf(__fmul_rn(nbr_alpha[static_cast<size_t>(i) * k + s], alpha_scale), 0.f);
+    if (a > 0.f) c = hash_lookup(nbr_ids[static_cast<size_t>(i) * k + s], keys, vals, cap);
+  }
+  const bool valid = c >= 0;
+  // ---- first touch of a column: no earlier valid slot (and not the own column) names it
+  bool first = valid && c != own;
+  for (int e = 0; e < G; ++e) {
+    const int ce = __shfl_sync(gmask, c, g0 + e);
+    if (e < s && ce == c) first = false;
+  }
+  // ---- weight of a first-touch slot: its alpha, then every later duplicate in slot order (fp32 adds, k order)
+  float w = a;
+  float w_own = 1.0f;  // slot 0: 1.0, then every neighbour that maps to the own column (self loops), in slot order
+  for (int e = 0; e < G; ++e) {
+    const int ce = __shfl_sync(gmask, c, g0 + e);
+    const float ae = __shfl_sync(gmask, a, g0 + e);
+    if (first && e > s && ce == c) w = __fadd_rn(w, ae);
+    if (ce >= 0 && ce == own) w_own = __fadd_rn(w_own, ae);
+  }
+  const unsigned first_mask = (__ballot_sync(gmask, first) >> g0) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+  const int cnt = 1 + __popc(first_mask);
+  const int out = 1 + __popc(first_mask & ((1u << s) - 1u));  // output slot of a first-touch lane
+  // ---- L1 norm in output-slot order (sequential fp32 adds, F.normalize(p=1), losses.py:110-111)
+  float tot = w_own;
+  for (unsigned m = first_mask; m; m &= m - 1) tot = __fadd_rn(tot, __shfl_sync(gmask, w, g0 + __ffs(m) - 1));
+  const float inv = 1.f / fmaxf(tot, 1e-12f);
+  if (!row_ok) return;
+  int* col_o = pos_col + static_cast<size_t>(i) * kp1;
+  float* w_o = pos_w + static_cast<size_t>(i) * kp1;
+  float* q_o = pos_q + static_cast<size_t>(i) * kp1;
+  if (s == 0) {
+    col_o[0] = own;
+    w_o[0] = w_own;
+    q_o[0] = w_own * inv;
+  }
+  if (first) {
+    col_o[out] = c;
+    w_o[out] = w;
+    q_o[out] = w * inv;
+  }
+  for (int t = cnt + s; t < kp1; t += G) {  // unused slots
+    col_o[t] = -1;
+    w_o[t] = 0.f;
+    q_o[t] = 0.f;
   }
 }
 
+// flag = 1 when the two gathered id vectors differ anywhere (flag is zeroed by the caller)
+__global__ void ids_differ_kernel(const long long* __restrict__ a, const long long* __restrict__ b, int n,
+                                  int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && a[i] != b[i]) *flag = 1;
+}
+// the hash kernels of the second direction do nothing when the id vectors are identical
+__global__ void hash_clear_if_kernel(long long* keys, int* vals, uint32_t cap, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= cap) {
+    keys[i] = kEmptyKey;
+    vals[i] = -1;
+  }
+}
+
+template <int G>
+static void launch_build_ell(const int64_t* nbr_ids, const float* nbr_alpha, int b_local, int k, float alpha_scale,
+                             int rank, const long long* keys, const int* vals, uint32_t cap, int32_t* pos_col,
+                             float* pos_w, float* pos_q, const int* copy_flag, const int32_t* src_col,
+                             const float* src_w, const float* src_q, cudaStream_t stream) {
+  const long long threads = static_cast<long long>(b_local) * G;
+  build_ell_kernel<G><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const long long*>(nbr_ids), nbr_alpha, b_local, k, alpha_scale, rank, keys, vals, cap, pos_col,
+      pos_w, pos_q, copy_flag, src_col, src_w, src_q);
+}
+
+// differ_flag / src_*: (second direction only) device flag that is 0 when this direction's id vector equals the other
+// direction's -- the hash kernels then return at once and the lists are copied from src_* -- or nullptr.
 cudaError_t launch_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids,
                                    const float* nbr_alpha, int b_local, int k, float alpha_scale, int rank,
                                    void* hash_ws, size_t hash_ws_bytes, int32_t* pos_col, float* pos_w, float* pos_q,
-                                   cudaStream_t stream) {
+                                   const int* differ_flag, const int32_t* src_col, const float* src_w,
+                                   const float* src_q, cudaStream_t stream) {
+  if (k > 32) return cudaErrorInvalidValue;
   const uint32_t cap = hash_capacity(n_global);
   long long* keys = static_cast<long long*>(hash_ws);
   int* vals = reinterpret_cast<int*>(keys + cap + 1);
   if (k > 0) {
     if (hash_ws == nullptr || hash_ws_bytes < positives_hash_bytes(n_global)) return cudaErrorInvalidValue;
-    hash_clear_kernel<<<(cap + 1 + 255) / 256, 256, 0, stream>>>(keys, vals, cap);
+    if (differ_flag != nullptr)
+      hash_clear_if_kernel<<<(cap + 1 + 255) / 256, 256, 0, stream>>>(keys, vals, cap, differ_flag);
+    else
+      hash_clear_kernel<<<(cap + 1 + 255) / 256, 256, 0, stream>>>(keys, vals, cap);
     hash_insert_kernel<<<(n_global + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const long long*>(all_ids),
-                                                                   n_global, keys, vals, cap);
+                                                                   n_global, keys, vals, cap, differ_flag);
   }
-  build_ell_kernel<<<(b_local + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const long long*>(nbr_ids), nbr_alpha,
-                                                             b_local, k, alpha_scale, rank, keys, vals, cap, pos_col,
-                                                             pos_w, pos_q);
+  if (k <= 8)
+    launch_build_ell<8>(nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, keys, vals, cap, pos_col, pos_w, pos_q,
+                        differ_flag, src_col, src_w, src_q, stream);
+  else if (k <= 16)
+    launch_build_ell<16>(nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, keys, vals, cap, pos_col, pos_w, pos_q,
+                         differ_flag, src_col, src_w, src_q, stream);
+  else
+    launch_build_ell<32>(nbr_ids, nbr_alpha, b_local, k, alpha_scale, rank, keys, vals, cap, pos_col, pos_w, pos_q,
+                         differ_flag, src_col, src_w, src_q, stream);
+  return cudaGetLastError();
+}
+cudaError_t launch_ids_differ(const int64_t* a, const int64_t* b, int n, int* flag, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  ids_differ_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const long long*>(a),
+                                                         reinterpret_cast<const long long*>(b), n, flag);
   return cudaGetLastError();
 }
 

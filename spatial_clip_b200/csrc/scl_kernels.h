@@ -65,7 +65,9 @@ cudaError_t launch_prep_scalars(const float* logit_scale, float cap, float* scal
 cudaError_t launch_build_positives(const int64_t* all_ids, int n_global, const int64_t* nbr_ids,
                                    const float* nbr_alpha, int b_local, int k, float alpha_scale, int rank,
                                    void* hash_ws, size_t hash_ws_bytes, int32_t* pos_col, float* pos_w, float* pos_q,
-                                   cudaStream_t stream);
+                                   const int* differ_flag, const int32_t* src_col, const float* src_w,
+                                   const float* src_q, cudaStream_t stream);
+cudaError_t launch_ids_differ(const int64_t* a, const int64_t* b, int n, int* flag, cudaStream_t stream);
 size_t positives_hash_bytes(int n_global);
 cudaError_t launch_row_finalize(const float4* partial, int n_slots, int m_pad, int m_rows, int d, const void* x_rows,
                                 const void* y_all, const int32_t* pos_col, const float* pos_q, int kp1,
