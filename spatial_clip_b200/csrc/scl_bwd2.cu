@@ -26,10 +26,9 @@ namespace scl {
 constexpr int kB2Rows = 64;     // rows per CTA (128 per pair)
 constexpr int kB2TileN = 256;   // columns per step (each CTA loads 128 of them for z)
 constexpr int kB2BK = 64;
-#ifndef SCL_B2_STAGES
-#define SCL_B2_STAGES 3
-#endif
-constexpr int kB2Stages = SCL_B2_STAGES;  // ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair
+// ring stages, each two 16 KB TMA boxes behind ONE full/empty barrier pair.  Measured (profiles/r2_bwd_lab.md): 2 stages
+// 2.29 ms, 3 stages 1.93 ms per launch at N = 32768; 3.5 stages (seven per-slot barriers) 1.97 ms -- more does not fit
+constexpr int kB2Stages = 3;
 constexpr int kB2SlotBytes = 16384;
 constexpr int kB2StageBytes = 2 * kB2SlotBytes;
 constexpr int kB2XChunkBytes = kB2Rows * kB2BK * 2;   // 8 KB
@@ -139,18 +138,10 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
       }
       int ring_s = 0;
       uint32_t ring_ph = 0;
-#ifdef SCL_LAB_NO_TMA
-      int lab_loads = 0;  // lab: only the first round of the ring is really loaded
-#endif
       // one ring stage = up to two 16 KB boxes from BOTH CTAs, all credited to the leader's full[s]
       auto acquire = [&](int bytes_per_cta) {
         const int s = ring_s;
         mbar_wait(&bars.empty[s], ring_ph ^ 1);
-#ifdef SCL_LAB_NO_TMA
-        if (lab_loads >= kB2Stages) {
-          if (leader) mbar_arrive(&bars.full[s]);
-        } else
-#endif
         if (leader) mbar_arrive_expect_tx(&bars.full[s], static_cast<uint32_t>(2 * bytes_per_cta));
         if (++ring_s == kB2Stages) {
           ring_s = 0;
@@ -158,13 +149,6 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         }
         return s;
       };
-#ifdef SCL_LAB_NO_TMA
-#define SCL_LAB_LOAD(...) do { if (lab_loads < kB2Stages) { __VA_ARGS__; } } while (0)
-#define SCL_LAB_STAGE_DONE() (++lab_loads)
-#else
-#define SCL_LAB_LOAD(...) do { __VA_ARGS__; } while (0)
-#define SCL_LAB_STAGE_DONE() ((void)0)
-#endif
       auto push_z = [&](int lt) {
         // this step's column coefficients {Lc, u', v', -} (4 KB) into this CTA's smem, one bulk copy
         const int cb = lt & 1;
@@ -176,20 +160,16 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         if (stream_x) {  // one K chunk per stage: Y chunk in slot 0, X chunk (8 KB) in slot 1
           for (int kc = 0; kc < nk; ++kc) {
             const int s = acquire(kB2SlotBytes + kB2XChunkBytes);
-            SCL_LAB_LOAD(
-                tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
-                tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK,
-                                 row0));
-            SCL_LAB_STAGE_DONE();
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes, &tm_cols, &bars.full[s], kc * kB2BK, col0);
+            tma_load_2d_pair(smem_ring + s * kB2StageBytes + kB2SlotBytes, &tm_rows, &bars.full[s], kc * kB2BK, row0);
           }
         } else {
           for (int kc = 0; kc < nk; kc += 2) {
             const int nb = min(2, nk - kc);
             const int s = acquire(nb * kB2SlotBytes);
             for (int b = 0; b < nb; ++b)
-              SCL_LAB_LOAD(tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
-                                            (kc + b) * kB2BK, col0));
-            SCL_LAB_STAGE_DONE();
+              tma_load_2d_pair(smem_ring + s * kB2StageBytes + b * kB2SlotBytes, &tm_cols, &bars.full[s],
+                               (kc + b) * kB2BK, col0);
           }
         }
       };
@@ -207,11 +187,9 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
               // two {64 d, 64 j} boxes of the row-major Y: this CTA's d range of group g, 64 columns j of the step
               const int dbase = p_d0 + d0 + 256 * g + static_cast<int>(cta) * (n_g / 2);
               uint8_t* slot = smem_ring + s * kB2StageBytes + b * kB2SlotBytes;
-              SCL_LAB_LOAD(
-                  tma_load_2d_pair(slot, &tm_cols_mn, &bars.full[s], dbase, col0 + js * 64);
-                  tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.full[s], dbase + 64, col0 + js * 64));
+              tma_load_2d_pair(slot, &tm_cols_mn, &bars.full[s], dbase, col0 + js * 64);
+              tma_load_2d_pair(slot + kB2SlotBytes / 2, &tm_cols_mn, &bars.full[s], dbase + 64, col0 + js * 64);
             }
-            SCL_LAB_STAGE_DONE();
           }
         }
       };
@@ -365,25 +343,13 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
       // dL/dz of one element (fp32): row term + column term, own-column soft target, ragged-edge mask
       auto g_of = [&](int j) {
         const float z = __uint_as_float(r[j]);
-#ifdef SCL_LAB_NO_EPI
-        return z;
-#else
-#ifdef SCL_LAB_NO_LDS
-        const float4 cc = make_float4(60.f + static_cast<float>(j), 1e-3f, 1e-4f, 0.f);
-#else
         const float4 cc = lds_v4(cf + static_cast<uint32_t>(j * 16));  // smem broadcast (same address across the warp)
-#endif
         const float p = ex2_approx(fmaf(z, s2, neg_lr));
-#ifdef SCL_LAB_ONE_EX2
-        const float pc = p * cc.x;
-#else
         const float pc = ex2_approx(fmaf(z, s2, -cc.x));
-#endif
         float g = fmaf(pc, fmaf(cc.z, z, cc.y), p * fmaf(rc.z, z, rc.y));
         if (has_diag) g -= (j == diag_col - col0) ? rc.w : 0.f;
         if (ragged) g = (col0 + j < n_cols) ? g : 0.f;
         return g;
-#endif
       };
       if constexpr (kSplit != 0) {
         // fp32-accurate mode: G = G1 + G2 (two bf16 tiles).  z already sits in registers, so TMEM goes back first;
@@ -425,18 +391,12 @@ bwd_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_rows,     // X [M, k
         }
         // single G buffer: the second GEMM of the previous step must have consumed it
         mbar_wait_warp(&bars.g_empty, (lt & 1) ^ 1);
-#ifndef SCL_LAB_NO_STS
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)  // K-major SWIZZLE_128B: 16-byte chunk XOR (row % 8)
           sts_v4(g_u32 + g_off + static_cast<uint32_t>(((c16 + ch) ^ (r_loc & 7)) * 16), packed[ch * 4 + 0],
                  packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-#else
-        if (packed[0] == 0x12345678u && packed[7] == 0x9abcdef0u) sts_v4(g_u32 + g_off, packed[0], packed[1], packed[2], packed[3]);
-#endif
       }
-#ifndef SCL_LAB_NO_FENCE
       fence_proxy_async();
-#endif
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(&bars.g_full);
