@@ -359,10 +359,11 @@ def run_ours(args):
     ms = marks[0].elapsed_time(marks[-1]) / args.steps
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     med = per_step[len(per_step) // 2]
-    t = torch.tensor([ms, med], device=dev)
+    t = torch.tensor([ms, med, per_step[0], per_step[int(0.9 * (len(per_step) - 1))], per_step[-1]], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, med = float(t[0].item()), float(t[1].item())
+    step_spread = {"min": float(t[2]), "p90": float(t[3]), "max": float(t[4])}
     loss_val = float(loss.detach())
 
     # ---- host cost of a step: wall time to ENQUEUE ten steps on an idle device (no synchronisation inside); when this
@@ -534,7 +535,8 @@ def run_ours(args):
     line = {
         "metric": "contrastive loss fwd+bwd pairs/sec (global batch 32768, D=512)",
         "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "median_ms_per_step": med, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": ms, "median_ms_per_step": med, "step_ms_spread": step_spread, "higher_is_better": True,
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "bf16x2 (fp32-accurate: bf16 hi/lo operand pairs, fp32 accumulate)" if split else "bf16",
         "data": "synthetic", "config": {**workload_config(world), "precision": args.precision},
