@@ -19,6 +19,7 @@ sample of the same workload.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -349,11 +350,16 @@ def run_ours(args):
         sampler.start()
     launches0 = ops.launches
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # no cyclic-GC pauses inside the timed region: a multi-millisecond collection on ONE rank stalls every rank at the
+    # next exchange (the step is ~1 ms at 8 ranks); reference counting keeps freeing tensors as usual
+    gc.collect()
+    gc.disable()
     marks[0].record()
     for i in range(args.steps):
         loss, g_img, g_txt = step({k: v.detach() for k, v in dev_in.items()})
         marks[i + 1].record()
     sync_all()
+    gc.enable()
     launches = (ops.launches - launches0) // max(1, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms = marks[0].elapsed_time(marks[-1]) / args.steps
@@ -471,10 +477,13 @@ def run_ours(args):
         sync_all()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()
         t0.record()
         e2e_loop(e2e_steps, deferred)
         t1.record()
         sync_all()
+        gc.enable()
         return t0.elapsed_time(t1) / e2e_steps
 
     e2e_note = ("double-buffered H2D on a copy stream; every step's loss is copied D2H into pinned memory and read by "
