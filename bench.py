@@ -343,11 +343,14 @@ def run_ours(args):
     # ---- device-resident timing: W warm-up steps, then EXACTLY K steps in one timed region
     for _ in range(args.warmup):
         step({k: v.detach() for k, v in dev_in.items()})
-    sync_all()
+    # the clock sampler starts BEFORE the barrier that aligns the ranks: NVML initialisation takes 5-20 ms on rank 0,
+    # and a rank that enters the timed loop late makes every other rank's first step wait for it at the first exchange
+    # (measured: one 18 ms step out of 50 at 8 ranks)
     sampler = NvmlSampler(dev)
     if rank == 0 and not sampler.start():  # no NVML binding / handle: nvidia-smi loop instead
         sampler = ClockSampler(local_rank)
         sampler.start()
+    sync_all()
     launches0 = ops.launches
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     # no cyclic-GC pauses inside the timed region: a multi-millisecond collection on ONE rank stalls every rank at the
