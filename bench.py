@@ -350,13 +350,13 @@ def run_ours(args):
     if rank == 0 and not sampler.start():  # no NVML binding / handle: nvidia-smi loop instead
         sampler = ClockSampler(local_rank)
         sampler.start()
+    # no cyclic-GC pauses inside the timed region either: a multi-millisecond collection on ONE rank stalls every rank
+    # at the next exchange (the step is ~1 ms at 8 ranks); reference counting keeps freeing tensors as usual
+    gc.collect()
+    gc.disable()
     sync_all()
     launches0 = ops.launches
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    # no cyclic-GC pauses inside the timed region: a multi-millisecond collection on ONE rank stalls every rank at the
-    # next exchange (the step is ~1 ms at 8 ranks); reference counting keeps freeing tensors as usual
-    gc.collect()
-    gc.disable()
     marks[0].record()
     for i in range(args.steps):
         loss, g_img, g_txt = step({k: v.detach() for k, v in dev_in.items()})
@@ -477,11 +477,11 @@ def run_ours(args):
 
     def time_e2e(deferred):
         e2e_loop(min(2, max(1, args.warmup)), deferred)
+        gc.collect()
+        gc.disable()
         sync_all()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
-        gc.collect()
-        gc.disable()
         t0.record()
         e2e_loop(e2e_steps, deferred)
         t1.record()
