@@ -335,19 +335,29 @@ def run_ours(args):
         out.backward()
         return out, img.grad, txt.grad
 
+    cpu_group = dist.new_group(backend="gloo") if (world > 1 and args.barrier == "gloo") else None
+
     def sync_all():
+        """Barrier over all ranks + device synchronisation (the bracket of every timed region).  With --barrier gloo
+        the rendezvous runs on a CPU process group: an eager NCCL collective between graph replays of the same
+        communicator showed up as one 10-18 ms step right after it."""
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group) if cpu_group is not None else dist.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident timing: W warm-up steps, then EXACTLY K steps in one timed region
+    # (the warm-up keeps each step's results alive into the next step exactly like the timed loop does, so that the
+    # caching allocator already owns two sets of gradient buffers: otherwise the SECOND timed step calls cudaMalloc --
+    # measured as one 10-25 ms step per run, which every rank then waits for)
+    loss = g_img = g_txt = None
     for _ in range(args.warmup):
-        step({k: v.detach() for k, v in dev_in.items()})
+        loss, g_img, g_txt = step({k: v.detach() for k, v in dev_in.items()})
     # the clock sampler starts BEFORE the barrier that aligns the ranks: NVML initialisation takes 5-20 ms on rank 0,
     # and a rank that enters the timed loop late makes every other rank's first step wait for it at the first exchange
     # (measured: one 18 ms step out of 50 at 8 ranks)
-    sampler = NvmlSampler(dev)
-    if rank == 0 and not sampler.start():  # no NVML binding / handle: nvidia-smi loop instead
+    sampler = NvmlSampler(dev, period_s=max(args.sampler_period_ms, 0.5) * 1e-3)
+    if rank == 0 and args.sampler_period_ms > 0 and not sampler.start():  # no NVML binding: nvidia-smi loop instead
         sampler = ClockSampler(local_rank)
         sampler.start()
     # no cyclic-GC pauses inside the timed region either: a multi-millisecond collection on ONE rank stalls every rank
@@ -364,15 +374,19 @@ def run_ours(args):
     sync_all()
     gc.enable()
     launches = (ops.launches - launches0) // max(1, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and args.sampler_period_ms > 0) else None
     ms = marks[0].elapsed_time(marks[-1]) / args.steps
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    raw_steps = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    per_step = sorted(raw_steps)
     med = per_step[len(per_step) // 2]
-    t = torch.tensor([ms, med, per_step[0], per_step[int(0.9 * (len(per_step) - 1))], per_step[-1]], device=dev)
+    slow = float(sum(1 for v in raw_steps if v > 1.5 * med))  # steps more than 1.5x this rank's median
+    t = torch.tensor([ms, med, per_step[0], per_step[int(0.9 * (len(per_step) - 1))], per_step[-1], slow], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, med = float(t[0].item()), float(t[1].item())
-    step_spread = {"min": float(t[2]), "p90": float(t[3]), "max": float(t[4])}
+    step_spread = {"min": float(t[2]), "p90": float(t[3]), "max": float(t[4]), "steps_over_1.5x_median": int(t[5]),
+                   "rank0_first_steps": [round(v, 3) for v in raw_steps[:4]],
+                   "rank0_slowest_step_index": int(max(range(len(raw_steps)), key=lambda i: raw_steps[i]))}
     loss_val = float(loss.detach())
 
     # ---- host cost of a step: wall time to ENQUEUE ten steps on an idle device (no synchronisation inside); when this
@@ -476,7 +490,7 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 20))
 
     def time_e2e(deferred):
-        e2e_loop(min(2, max(1, args.warmup)), deferred)
+        e2e_loop(min(4, max(1, args.warmup)), deferred)
         gc.collect()
         gc.disable()
         sync_all()
@@ -616,6 +630,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)  # 10 warm-up + 50 timed
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--sampler-period-ms", type=float, default=2.0, help="clock sampler period; 0 = no sampler")
+    ap.add_argument("--barrier", choices=["nccl", "gloo"], default="nccl",
+                    help="process group of the barriers that bracket the timed regions")
     ap.add_argument("--no-graphs", action="store_true", help="run every step eagerly (no CUDA-graph replay)")
     ap.add_argument("--timeline", action="store_true", help="add the per-phase GPU times of one step to the JSON line")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
