@@ -602,3 +602,43 @@ def test_no_grad_forward_replays_too(ops):
             a = mod(b.image_features.cuda(), b.text_features.cuda(), s)["contrastive_loss"]
             c = ref(b.image_features.cuda(), b.text_features.cuda(), s)["contrastive_loss"]
         assert torch.equal(a, c)
+
+
+# ---------------------------------------------------------------- more neighbour slots than the default 8
+@pytest.mark.parametrize("k", [12, 20, 31])
+def test_positive_lists_with_many_neighbour_slots(ops, k):
+    """K > 8 runs the 16- / 32-lane builder groups: the lists must equal the oracle's dense labels and the host
+    producer's lists bit for bit, and the module must still match the oracle."""
+    from spatial_clip_b200 import SpatialLoss
+    from spatial_clip_b200.positives import resolve_positive_columns
+
+    n, d = 384, 128
+    b = make_spot_batch(n=n, d=d, k=k, seed=700 + k, dup_frac=0.05, self_loops=True, negative_alphas=True)
+    col, w, q = ops.build_positives(b.tile_ids.cuda(), b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda(), n, k, 0.5, 0,
+                                    b.image_features.cuda())
+    torch.cuda.synchronize()
+    rows, _ = soft_label_triples(b.tile_ids.numpy(), b.neighbor_tile_ids.numpy(), b.neighbor_alphas.numpy(), 0.5, 0)
+    want = dense_labels(rows, n)
+    got = np.zeros_like(want)
+    c_np, w_np = col.cpu().numpy(), w.cpu().numpy()
+    for i in range(n):
+        for t in range(k + 1):
+            if c_np[i, t] >= 0:
+                got[i, c_np[i, t]] = w_np[i, t]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    hc, hw, hq = resolve_positive_columns(b.tile_ids, b.neighbor_tile_ids, b.neighbor_alphas, 0.5)
+    assert torch.equal(col.cpu(), hc) and torch.equal(w.cpu().view(torch.int32), hw.view(torch.int32))
+    assert torch.equal(q.cpu().view(torch.int32), hq.view(torch.int32))
+    img = b.image_features.cuda().requires_grad_(True)
+    txt = b.text_features.cuda().requires_grad_(True)
+    s = torch.tensor(30.0, device="cuda", requires_grad=True)
+    ids = b.tile_ids.cuda()
+    loss = SpatialLoss(cap_logit_scale=40.0, temp_reg_weight=0.05, neighbor_alpha_scale=0.5)(
+        img, txt, s, ids, ids.clone(), b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())["contrastive_loss"]
+    loss.backward()
+    orc = spatial_loss_oracle(b.image_features.bfloat16().float().numpy(), b.text_features.bfloat16().float().numpy(), 30.0,
+                              b.tile_ids.numpy(), b.tile_ids.numpy(), b.neighbor_tile_ids.numpy(),
+                              b.neighbor_alphas.numpy(), 1, 40.0, 0.05, 0.5)
+    assert abs(float(loss.detach()) - orc.ranks[0].loss) <= 2e-5 * abs(orc.ranks[0].loss) + 6e-5
+    for got_g, ref in ((img.grad.cpu().numpy(), orc.d_image), (txt.grad.cpu().numpy(), orc.d_text)):
+        assert np.abs(got_g - ref).max() <= 5e-3 * np.abs(ref).max()
