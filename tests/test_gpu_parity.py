@@ -238,6 +238,25 @@ def test_bf16_inputs_give_bf16_grads(ops):
     assert np.abs(img.grad.float().cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
 
 
+def test_fp16_inputs_give_fp16_grads(ops):
+    """Half-precision features take the same path (cast to bf16 operands, fp32 statistics); the gradient comes back
+    in the input dtype through bwd_gather_kernel<__half>."""
+    meta, gold = load_golden("spatial_n300_d256")
+    from spatial_clip_b200 import SpatialLoss
+
+    b = make_spot_batch(**meta["gen"])
+    img = b.image_features.cuda().half().requires_grad_(True)
+    txt = b.text_features.cuda().half().requires_grad_(True)
+    s = torch.tensor(float(meta["scale"]), device="cuda", requires_grad=True)
+    out = SpatialLoss(**meta["ctor"])(img, txt, s, b.tile_ids.cuda(), b.tile_ids.cuda(), b.neighbor_tile_ids.cuda(),
+                                      b.neighbor_alphas.cuda())
+    out["contrastive_loss"].backward()
+    assert img.grad.dtype == torch.float16 and txt.grad.dtype == torch.float16
+    assert abs(float(out["contrastive_loss"].detach()) - gold["loss"][0]) <= 2e-3 * abs(gold["loss"][0])
+    for got, ref in ((img.grad, gold["d_image"]), (txt.grad, gold["d_text"])):
+        assert np.abs(got.float().cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+
+
 def test_no_grad_forward_only(ops):
     meta, gold = load_golden("clip_n300_d256")
     from spatial_clip_b200 import ClipLoss

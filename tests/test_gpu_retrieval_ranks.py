@@ -50,3 +50,30 @@ def test_ranks_match_dense_count(ops, n, d, k_nbr):
         got = recall_at_k(ranks, k).item()
         ref = (want < min(k, n)).float().mean().item()
         assert abs(got - ref) <= 2.0 / n
+
+
+def test_ranks_under_graph_replay(ops):
+    """From the third call on the module replays a captured graph; the ranks buffer is then the graph's static output
+    ("of the last call") and must equal the eager module's on every step, with gradients flowing as usual."""
+    from spatial_clip_b200 import SpatialLoss
+
+    n, d, k = 1200, 256, 8
+    graphed = SpatialLoss(track_retrieval_ranks=True, temp_reg_weight=0.05)
+    eager = SpatialLoss(track_retrieval_ranks=True, temp_reg_weight=0.05, cuda_graphs=False)
+    for step in range(5):
+        b = make_spot_batch(n=n, d=d, k=k, seed=900 + step)
+        noise = torch.nn.functional.normalize(torch.randn(n, d, generator=torch.Generator().manual_seed(step)), dim=-1)
+        txt0 = torch.nn.functional.normalize(0.3 * b.image_features + noise, dim=-1)
+        got = []
+        for mod in (graphed, eager):
+            img = b.image_features.cuda().requires_grad_(True)
+            txt = txt0.cuda().requires_grad_(True)
+            s = torch.tensor(20.0, device="cuda", requires_grad=True)
+            ids = b.tile_ids.cuda()
+            out = mod(img, txt, s, ids, ids, b.neighbor_tile_ids.cuda(), b.neighbor_alphas.cuda())
+            out["contrastive_loss"].backward()
+            torch.cuda.synchronize()
+            got.append((mod.last_retrieval_ranks.clone(), img.grad.clone()))
+        assert torch.equal(got[0][0], got[1][0]), step
+        assert torch.equal(got[0][1], got[1][1]), step
+        assert got[0][0].shape == (n,) and int(got[0][0].max()) > 0
