@@ -1,8 +1,9 @@
 """One process per GPU over NCCL against the reference's multi-rank goldens: every local_loss / gather_with_grad
 combination of ClipLoss (reference: src/open_clip/loss.py:21-65, :120-155) and the SpatialLoss fixtures
 (src/models/components/losses.py:73-122), five steps per module so that the eager route (steps 0-1) and the CUDA-graph
-replay with its captured all-gathers (steps 2-4) are both compared.  Needs as many GPUs as the fixture has ranks:
-skipped on a smaller box (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_nccl.py -m gpu`).
+replay with its captured all-gathers (steps 2-4) are both compared.  The two-rank fixtures only (4 / 8 ranks over
+NCCL are covered by bench.py's parity block, profiles/r2_bench_{4,8}gpu.json); skipped on a one-GPU box
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_nccl.py -m gpu`).
 """
 import socket
 
@@ -64,7 +65,7 @@ def _nccl_worker(rank, world, port, name, q):
         q.put((rank, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if "_w2" in n or "_w4" in n or "_w8" in n])
+@pytest.mark.parametrize("name", golden_names(world=2))
 def test_nccl_ranks_match_reference(name):
     import torch.multiprocessing as mp
 
