@@ -281,6 +281,9 @@ class _GraphedStep:
 
 
 _GRAPHS: Dict[tuple, _GraphedStep] = {}
+# Every captured configuration owns a private memory pool (static inputs, gathered operands, partials).  A job has a
+# handful of configurations (train / eval batch, the ragged last batch); beyond this many, new ones run eagerly.
+_MAX_GRAPHED_CONFIGS = 16
 
 
 def release_cuda_graphs():
@@ -350,9 +353,10 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if positives is None and _graphs_usable(ops, cfg, ins):
             same_ids = cfg.kind == "spatial" and image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
             key = _graph_key(cfg, ins, (need_backward, same_ids, tuple(ctx.needs_input_grad[:3])))
-            step = _GRAPHS.setdefault(key, _GraphedStep())
-            if step.broken:
-                step = None
+            if key in _GRAPHS or len(_GRAPHS) < _MAX_GRAPHED_CONFIGS:
+                step = _GRAPHS.setdefault(key, _GraphedStep())
+                if step.broken:
+                    step = None
         if step is not None:
             step.calls += 1
             if step.calls <= step.WARMUP:
