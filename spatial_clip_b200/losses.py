@@ -281,8 +281,9 @@ class _GraphedStep:
 
 
 _GRAPHS: Dict[tuple, _GraphedStep] = {}
-# Every captured configuration owns a private memory pool (static inputs, gathered operands, partials).  A job has a
-# handful of configurations (train / eval batch, the ragged last batch); beyond this many, new ones run eagerly.
+# Every CAPTURED configuration owns a private memory pool (static inputs, gathered operands, partials).  A job has a
+# handful of configurations (train / eval batch, the ragged last batch); beyond this many captures, new ones run
+# eagerly.  (Configurations still in their eager warm-up calls do not count.)
 _MAX_GRAPHED_CONFIGS = 16
 
 
@@ -353,13 +354,15 @@ class _ContrastiveLossFn(torch.autograd.Function):
         if positives is None and _graphs_usable(ops, cfg, ins):
             same_ids = cfg.kind == "spatial" and image_tile_ids.data_ptr() == text_tile_ids.data_ptr()
             key = _graph_key(cfg, ins, (need_backward, same_ids, tuple(ctx.needs_input_grad[:3])))
-            if key in _GRAPHS or len(_GRAPHS) < _MAX_GRAPHED_CONFIGS:
-                step = _GRAPHS.setdefault(key, _GraphedStep())
-                if step.broken:
-                    step = None
+            step = _GRAPHS.setdefault(key, _GraphedStep())
+            if step.broken:
+                step = None
         if step is not None:
             step.calls += 1
             if step.calls <= step.WARMUP:
+                step = None
+            elif step.fwd is None and sum(st.fwd is not None for st in _GRAPHS.values()) >= _MAX_GRAPHED_CONFIGS:
+                step.broken = True  # this configuration stays eager
                 step = None
         if step is None:
             out4, lists, ranks, saved, c = _forward_impl(ops, cfg, img_in, txt_in, scale, image_tile_ids, text_tile_ids,

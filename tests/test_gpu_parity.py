@@ -555,8 +555,9 @@ def test_graph_replay_is_bitwise_identical_to_eager(ops, kind):
     """After two eager calls per configuration the modules replay forward and backward as CUDA graphs: same kernels
     on the same values, so every step must equal the eager module bit for bit -- with inputs that change from step to
     step and live at different addresses."""
-    from spatial_clip_b200 import ClipLoss, SpatialLoss
+    from spatial_clip_b200 import ClipLoss, SpatialLoss, release_cuda_graphs
 
+    release_cuda_graphs()  # independent of what earlier tests of this process captured (the cache is bounded)
     n, d, k = 1500, 256, 8
     cfg = dict(local_loss=True, gather_with_grad=True, cap_logit_scale=40.0, temp_reg_weight=0.05,
                neighbor_alpha_scale=0.5, float32_logits=True)
@@ -591,8 +592,9 @@ def test_graph_replay_is_bitwise_identical_to_eager(ops, kind):
 
 
 def test_graph_buffers_guard_against_out_of_order_backward(ops):
-    from spatial_clip_b200 import ClipLoss
+    from spatial_clip_b200 import ClipLoss, release_cuda_graphs
 
+    release_cuda_graphs()
     mod = ClipLoss()
     b = make_spot_batch(n=512, d=128, k=0, seed=5)
 
